@@ -1,0 +1,127 @@
+/*
+ * mcb200.h - C ABI of the B200-native gate-level evaluation engine (libmcb200.so).
+ *
+ * Drop-in boundary for the simulation path of matijakevic/mcircuit.  The reference has no
+ * FFI of its own: its Python `JIT` object obtains two raw function pointers from LLVM MCJIT
+ * and calls them through ctypes (`CFUNCTYPE(None)`), and peeks/pokes net storage through
+ * `get_global_value_address` + a `c_ulonglong` cast.  Each entry point below names the
+ * reference interface it replaces as `core/simulator.py:<line>`.
+ *
+ * Conventions
+ *   - plain C types only; every `d_` pointer is a DEVICE pointer owned by the caller (the
+ *     Python host keeps them alive as torch tensors); `h_` pointers are host memory;
+ *   - the library allocates no persistent device memory; `mcb_plan` is a host-side handle
+ *     (a CUDA graph) that only remembers the pointers it was given;
+ *   - every call returns 0 on success or a negative code; `mcb_last_error()` returns the
+ *     message of the calling thread's last failure; no C++ exception crosses the boundary;
+ *   - all calls are asynchronous enqueues on `stream` (a `cudaStream_t` passed as `void*`,
+ *     NULL = the legacy default stream) unless stated otherwise.
+ *
+ * Data layout: one 64-bit word carries one wire for 64 stimulus lanes.
+ * State is slot-major: `word(slot, column)`.  Slots `< n_persist` live in the persistent
+ * plane `d_persist[slot * persist_stride + column]`; slots `>= n_persist` live in the
+ * scratch plane `d_scratch[(slot - n_persist) * scratch_stride + column]` and are recycled
+ * by liveness.  A netlist record is 16 bytes, `uint32 {op | in2 << 8, in0, in1, out}`;
+ * records are sorted by level and `level_off[l] .. level_off[l+1]` delimits level `l`.
+ */
+#ifndef MCB200_H
+#define MCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCB_VERSION 1
+
+/* opcodes (low 7 bits of record word 0); bit 7 complements the result */
+enum {
+    MCB_OP_NOP = 0,  MCB_OP_BUF = 1,  MCB_OP_AND = 2,  MCB_OP_OR = 3,   MCB_OP_XOR = 4,
+    MCB_OP_ANDN = 5, MCB_OP_MUX = 6,  MCB_OP_AND3 = 7, MCB_OP_OR3 = 8,  MCB_OP_XOR3 = 9,
+    MCB_OP_MAJ = 10, MCB_OP_NEG = 0x80
+};
+
+/* error codes */
+enum {
+    MCB_OK = 0, MCB_ERR_ARG = -1, MCB_ERR_CUDA = -2, MCB_ERR_NO_DEVICE = -3,
+    MCB_ERR_ARCH = -4, MCB_ERR_STATE = -5
+};
+
+/* where the lane words of a tile live */
+typedef struct mcb_state {
+    uint64_t *d_persist;      /* first column of this tile, slot 0                      */
+    int64_t   persist_stride; /* words between consecutive persistent slots             */
+    uint64_t *d_scratch;      /* first column of this tile's scratch, slot n_persist    */
+    int64_t   scratch_stride; /* words between consecutive scratch slots                */
+    int32_t   n_persist;      /* slots below this number are persistent                 */
+    int32_t   n_slots;        /* n_persist + scratch slots (bounds checking only)       */
+    int64_t   n_words;        /* columns (64-lane words) in this tile                   */
+} mcb_state;
+
+int         mcb_version(void);
+const char *mcb_last_error(void);
+/* sm count, compute capability, memory; fails with MCB_ERR_ARCH unless the device is sm_100 */
+int mcb_device_info(int device, int *sm_count, int *cc_major, int *cc_minor,
+                    int64_t *total_mem, int64_t *l2_bytes);
+
+/* K1 - levelized evaluation.  Replaces the body of the JIT'd `step()` for every primitive
+ * (core/simulator.py:195-223 driving :77-147): evaluates levels [level_begin, level_end)
+ * of the netlist on one lane tile, one launch per level.                                 */
+int mcb_eval_levels(const uint32_t *d_records, const int32_t *h_level_off,
+                    int level_begin, int level_end, const mcb_state *st, void *stream);
+
+/* K2 - fused end-of-step latch.  Replaces the implicit "a fan-in whose driver is emitted
+ * later sees the previous step's value" of the reference's in-place globals
+ * (core/simulator.py:41-53, :185-191): runs `n` BUF records (cur -> prev shadow).  The
+ * compiler also appends these as the last level, so mcb_eval_levels/mcb_run already
+ * include them; this entry exists for callers that drive levels themselves.             */
+int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void *stream);
+
+/* K3 - resident multi-step run.  Replaces `burst()` (core/simulator.py:225-245, :296-297)
+ * without its off-by-one: runs exactly `steps` steps; the Python `burst()` passes
+ * burst_size + 1.  mode 0: one persistent kernel, each thread owns lane columns and walks
+ * the whole record stream (every level padded by the host to a multiple of
+ * MCB_RESIDENT_UNROLL records with NOPs, so a batch never straddles a level); mode 1: per-level launches captured once in a
+ * CUDA graph and replayed `steps` times.                                                  */
+#define MCB_RESIDENT_UNROLL 4
+int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
+            const mcb_state *st, int64_t steps, int mode, void *stream);
+
+/* K4 - signatures and toggle counts (new capability; no reference counterpart - the
+ * reference only peeks one pin at a time, core/simulator.py:285-287).  For each of `n`
+ * persistent slots: d_popcount[i] += number of set lane bits, d_checksum[i] += sum over
+ * columns j of word * (2 * (col_offset + j) + 1) mod 2^64.  Both are sums, so per-GPU
+ * vectors combine with ncclSum.  Columns >= n_words are ignored.                         */
+int mcb_signature(const int32_t *d_slots, int n, const mcb_state *st, int64_t col_offset,
+                  uint64_t *d_popcount, uint64_t *d_checksum, void *stream);
+/* d_toggles[i] += popcount(word ^ shadow); shadow = word, per slot and column            */
+int mcb_toggle_accum(const int32_t *d_slots, int n, const mcb_state *st,
+                     uint64_t *d_shadow, int64_t shadow_stride, uint64_t *d_toggles,
+                     void *stream);
+
+/* K5 - stimulus and packing.  Generalise `set_pin_state` / `get_pin_state`
+ * (core/simulator.py:285-291) from one lane to all lanes.                                 */
+/* word(slot i, column j) = splitmix64(seed ^ (streams[i] << 32) ^ (col_offset + j))       */
+int mcb_stimulus(const int32_t *d_slots, const int32_t *d_streams, int n, const mcb_state *st,
+                 int64_t col_offset, uint64_t seed, void *stream);
+/* every column of slot i = d_values[i] (0 / ~0 broadcast for scalar pokes, constants)     */
+int mcb_fill_rows(const int32_t *d_slots, const uint64_t *d_values, int n,
+                  const mcb_state *st, void *stream);
+/* values-per-lane -> bit planes: lane l of d_values (n_lanes = 64 * n_words values of
+ * `width` bits) goes to bit (l % 64) of column (l / 64) of slots d_slots[0..width)        */
+int mcb_pack(const uint64_t *d_values, int width, const int32_t *d_slots,
+             const mcb_state *st, void *stream);
+int mcb_unpack(uint64_t *d_values, int width, const int32_t *d_slots,
+               const mcb_state *st, void *stream);
+
+/* tuning knobs (block size, gates per block ...); returns the previous value              */
+int mcb_set_tuning(const char *key, int value);
+/* number of kernel launches this library has issued on this thread since the last reset   */
+int64_t mcb_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCB200_H */

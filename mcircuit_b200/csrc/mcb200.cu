@@ -1,0 +1,755 @@
+// mcb200.cu - hand-written sm_100a kernels + the C ABI of include/mcb200.h.
+//
+// Bit-sliced gate evaluation: one 64-bit word = one wire x 64 stimulus lanes, so every
+// AND/OR/XOR/NOT/MUX of the reference's step function (core/simulator.py:77-147) is one
+// bitwise instruction on a lane word.  State is slot-major (word(slot, column)); a level of
+// the netlist is a set of independent records {op|in2<<8, in0, in1, out}.  This is integer,
+// HBM-bound work: no tensor cores.  See DESIGN.md for the roofline of each kernel.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <atomic>
+
+#include "../../include/mcb200.h"
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+    do {                                                                                   \
+        cudaError_t e__ = (expr);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(MCB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                        __FILE__, __LINE__);                                               \
+    } while (0)
+
+#define LAUNCH_CHECK(name)                                                                 \
+    do {                                                                                   \
+        g_launches.fetch_add(1, std::memory_order_relaxed);                                \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(MCB_ERR_CUDA, "launch of %s failed: %s", name, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// tuning knobs
+// ------------------------------------------------------------------------------------------
+struct Tuning {
+    int level_block = 256;      // threads per CTA of the level kernel
+    int level_unroll = 4;       // records in flight per thread (1, 2, 4 or 8)
+    int level_ctas_per_sm = 0;  // 0: one record batch per CTA; n: persistent, grid ~ sms * n
+    int level_cache = 1;        // 0: default loads, 1: L1::no_allocate loads
+    int resident_block = 128;   // threads per CTA of the resident kernel
+    int resident_tma = 1;       // stage the record stream with cp.async.bulk + mbarrier
+    int resident_smem = 1;      // keep state in shared memory when it fits
+    int graph_min_steps = 2;    // mode 1: capture a graph when steps >= this
+};
+static Tuning g_tune;
+static int g_sm_count = 0;
+
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
+        g_sm_count = p.multiProcessorCount;
+    }
+    return g_sm_count;
+}
+
+// ------------------------------------------------------------------------------------------
+// device helpers
+// ------------------------------------------------------------------------------------------
+struct View {
+    uint64_t *persist;
+    long long pstride;
+    uint64_t *scratch_biased;   // scratch - n_persist * sstride, so both planes index by slot
+    long long sstride;
+    uint32_t n_persist;
+    long long n_words;
+};
+
+static View make_view(const mcb_state *st) {
+    View v;
+    v.persist = st->d_persist;
+    v.pstride = st->persist_stride;
+    v.sstride = st->scratch_stride;
+    v.scratch_biased = st->d_scratch ? st->d_scratch - (long long)st->n_persist * st->scratch_stride
+                                     : nullptr;
+    v.n_persist = (uint32_t)st->n_persist;
+    v.n_words = st->n_words;
+    return v;
+}
+
+__device__ __forceinline__ uint64_t *row(const View &v, uint32_t slot) {
+    return slot < v.n_persist ? v.persist + (long long)slot * v.pstride
+                              : v.scratch_biased + (long long)slot * v.sstride;
+}
+
+__device__ __forceinline__ uint64_t apply_op(uint32_t op, uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    switch (op & 0x7f) {
+        case MCB_OP_BUF:  r = a; break;
+        case MCB_OP_AND:  r = a & b; break;
+        case MCB_OP_OR:   r = a | b; break;
+        case MCB_OP_XOR:  r = a ^ b; break;
+        case MCB_OP_ANDN: r = a & ~b; break;
+        case MCB_OP_MUX:  r = (a & b) | (~a & c); break;
+        case MCB_OP_AND3: r = a & b & c; break;
+        case MCB_OP_OR3:  r = a | b | c; break;
+        case MCB_OP_XOR3: r = a ^ b ^ c; break;
+        case MCB_OP_MAJ:  r = (a & b) | (a & c) | (b & c); break;
+        default:          r = 0; break;
+    }
+    return (op & MCB_OP_NEG) ? ~r : r;
+}
+
+template <int CACHE>
+__device__ __forceinline__ ulonglong2 ld_state2(const uint64_t *p) {
+    ulonglong2 r;
+    if (CACHE == 1) {
+        asm volatile("ld.global.L1::no_allocate.v2.u64 {%0, %1}, [%2];"
+                     : "=l"(r.x), "=l"(r.y) : "l"(p));
+    } else {
+        asm volatile("ld.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+    }
+    return r;
+}
+
+__device__ __forceinline__ void st_state2(uint64_t *p, ulonglong2 v) {
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(v.x), "l"(v.y) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: one level.  Thread = one 16-byte column pair; grid.x covers the tile's columns,
+// grid.y strides over the level's records U at a time.  All 2U (3U) row loads of a batch are
+// issued before the first use, so each thread keeps U*32..48 bytes in flight; a warp reads
+// 512 contiguous bytes of each fan-in row and the record itself is one broadcast 16-byte
+// load (uniform across the CTA).
+// ------------------------------------------------------------------------------------------
+template <int U, int CACHE>
+__global__ void __launch_bounds__(256)
+k_eval_level(const uint4 *__restrict__ recs, int n_recs, View v, long long n_vec) {
+    const long long col = ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (col >= n_vec) return;
+    const long long off = col * 2;
+    for (int g0 = blockIdx.y * U; g0 < n_recs; g0 += gridDim.y * U) {
+        uint4 r[U];
+        ulonglong2 a[U], b[U], c[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            r[u] = (g0 + u < n_recs) ? __ldg(recs + g0 + u) : make_uint4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t op = r[u].x & 0x7f;
+            a[u] = b[u] = c[u] = make_ulonglong2(0, 0);
+            if (op != MCB_OP_NOP) {
+                a[u] = ld_state2<CACHE>(row(v, r[u].y) + off);
+                if (op != MCB_OP_BUF) b[u] = ld_state2<CACHE>(row(v, r[u].z) + off);
+                if (op >= MCB_OP_MUX) c[u] = ld_state2<CACHE>(row(v, r[u].x >> 8) + off);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const uint32_t op = r[u].x & 0xff;
+            if ((op & 0x7f) != MCB_OP_NOP) {
+                ulonglong2 o;
+                o.x = apply_op(op, a[u].x, b[u].x, c[u].x);
+                o.y = apply_op(op, a[u].y, b[u].y, c[u].y);
+                st_state2(row(v, r[u].w) + off, o);
+            }
+        }
+    }
+}
+
+template <int U, int CACHE>
+static void launch_level_t(const uint4 *recs, int n, const View &v, cudaStream_t s) {
+    const long long n_vec = (v.n_words + 1) / 2;
+    int block = g_tune.level_block;
+    if (block > 256) block = 256;
+    if (block < 32) block = 32;
+    while (block > 32 && block / 2 >= n_vec) block /= 2;
+    const long long gx = (n_vec + block - 1) / block;
+    const long long max_gy = (n + U - 1) / U;
+    long long gy = max_gy;
+    if (g_tune.level_ctas_per_sm > 0) {
+        const long long want = (long long)sm_count() * g_tune.level_ctas_per_sm * (256 / block);
+        gy = (want + gx - 1) / gx;
+        if (gy > max_gy) gy = max_gy;
+    }
+    if (gy < 1) gy = 1;
+    if (gy > 65535) gy = 65535;
+    dim3 grid((unsigned)gx, (unsigned)gy, 1);
+    k_eval_level<U, CACHE><<<grid, block, 0, s>>>(recs, n, v, n_vec);
+}
+
+static int launch_level(const uint4 *recs, int n, const View &v, cudaStream_t s) {
+    if (n <= 0) return 0;
+    const int U = g_tune.level_unroll;
+    const int C = g_tune.level_cache ? 1 : 0;
+#define MCB_LL(UU)                                                                         \
+    do {                                                                                   \
+        if (C) launch_level_t<UU, 1>(recs, n, v, s);                                       \
+        else launch_level_t<UU, 0>(recs, n, v, s);                                         \
+    } while (0)
+    if (U >= 8) MCB_LL(8);
+    else if (U >= 4) MCB_LL(4);
+    else if (U >= 2) MCB_LL(2);
+    else MCB_LL(1);
+#undef MCB_LL
+    LAUNCH_CHECK("k_eval_level");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K3 (mode 0): resident run.  Lanes never interact, so a thread that owns a lane column can
+// walk the whole record stream for many steps with no barrier at all: "level" only bounds
+// which records may be batched (the host pads every level to a multiple of RU records, so a
+// batch never straddles a level and its loads may all be issued before its stores).  The
+// record stream - the same for every thread - is staged through shared memory in chunks by
+// one TMA bulk copy per chunk (cp.async.bulk + mbarrier, double buffered); state words are
+// either in global memory (L1/L2-resident across steps when small) or, when the whole slot
+// file of the CTA's columns fits, in shared memory for the entire run.
+// ------------------------------------------------------------------------------------------
+#define RU MCB_RESIDENT_UNROLL
+#define REC_CHUNK 512                      // records per staged chunk (8 KB)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct GlobalCols {
+    View v;
+    long long col;
+    __device__ __forceinline__ uint64_t ld(uint32_t slot) const { return row(v, slot)[col]; }
+    __device__ __forceinline__ void st(uint32_t slot, uint64_t x) const { row(v, slot)[col] = x; }
+};
+
+// state in shared memory: word(slot, thread) at smem[slot * blockDim.x + threadIdx.x]
+struct SmemCols {
+    uint64_t *base;
+    int stride;
+    __device__ __forceinline__ uint64_t ld(uint32_t slot) const { return base[slot * stride]; }
+    __device__ __forceinline__ void st(uint32_t slot, uint64_t x) const { base[slot * stride] = x; }
+};
+
+template <class Cols>
+__device__ __forceinline__ void run_batch(const uint4 *r4, const Cols &cols) {
+    uint4 r[RU];
+    uint64_t a[RU], b[RU], c[RU];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) r[u] = r4[u];
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+        const uint32_t op = r[u].x & 0x7f;
+        a[u] = b[u] = c[u] = 0;
+        if (op != MCB_OP_NOP) {
+            a[u] = cols.ld(r[u].y);
+            if (op != MCB_OP_BUF) b[u] = cols.ld(r[u].z);
+            if (op >= MCB_OP_MUX) c[u] = cols.ld(r[u].x >> 8);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < RU; ++u) {
+        const uint32_t op = r[u].x & 0xff;
+        if ((op & 0x7f) != MCB_OP_NOP) cols.st(r[u].w, apply_op(op, a[u], b[u], c[u]));
+    }
+}
+
+template <bool TMA, bool SMEM_STATE>
+__global__ void __launch_bounds__(256)
+k_run_resident(const uint4 *__restrict__ recs, int n_recs, View v, long long steps, int n_slots) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint4 *rbuf = reinterpret_cast<uint4 *>(smem_raw);                  // [2][REC_CHUNK]
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * REC_CHUNK * sizeof(uint4));
+    uint64_t *sstate = reinterpret_cast<uint64_t *>(smem_raw + 2 * REC_CHUNK * sizeof(uint4) + 128);
+
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = col < v.n_words;
+    const int tid = threadIdx.x;
+    const int n_chunks = (n_recs + REC_CHUNK - 1) / REC_CHUNK;
+    const long long total = steps * (long long)n_chunks;
+
+    GlobalCols gcols{v, col};
+    SmemCols scols{sstate + tid, (int)blockDim.x};
+
+    if (SMEM_STATE) {
+        // bring this CTA's columns of every slot on chip once (coalesced: thread = column)
+        for (int s = 0; s < n_slots; ++s) scols.st(s, active ? gcols.ld(s) : 0ull);
+    }
+    if (TMA) {
+        if (tid == 0) {
+            mbar_init(&bars[0], 1);
+            mbar_init(&bars[1], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+        if (tid == 0 && total > 0) {
+            const int cnt = min(REC_CHUNK, n_recs);
+            mbar_expect_tx(&bars[0], cnt * 16);
+            bulk_g2s(rbuf, recs, cnt * 16, &bars[0]);
+        }
+    }
+    for (long long it = 0; it < total; ++it) {
+        const int chunk = (int)(it % n_chunks);
+        const int buf = (int)(it & 1);
+        const int base = chunk * REC_CHUNK;
+        const int cnt = min(REC_CHUNK, n_recs - base);
+        if (TMA) {
+            // prefetch the next chunk into the other buffer (free since the barrier below)
+            if (tid == 0 && it + 1 < total) {
+                const int nchunk = (int)((it + 1) % n_chunks);
+                const int nbase = nchunk * REC_CHUNK;
+                const int ncnt = min(REC_CHUNK, n_recs - nbase);
+                mbar_expect_tx(&bars[buf ^ 1], ncnt * 16);
+                bulk_g2s(rbuf + (buf ^ 1) * REC_CHUNK, recs + nbase, ncnt * 16, &bars[buf ^ 1]);
+            }
+            mbar_wait(&bars[buf], (uint32_t)((it >> 1) & 1));
+        } else {
+            for (int i = tid; i < cnt; i += blockDim.x) rbuf[buf * REC_CHUNK + i] = __ldg(recs + base + i);
+            __syncthreads();
+        }
+        const uint4 *rb = rbuf + buf * REC_CHUNK;
+        if (active) {
+            for (int i = 0; i < cnt; i += RU) {
+                if (SMEM_STATE) run_batch(rb + i, scols);
+                else run_batch(rb + i, gcols);
+            }
+        }
+        __syncthreads();     // everyone is done with rbuf[buf] before it is refilled
+    }
+    if (SMEM_STATE) {
+        if (active)
+            for (int s = 0; s < n_slots; ++s) gcols.st(s, scols.ld(s));
+    }
+}
+
+static int launch_resident(const uint4 *recs, int n_recs, const View &v, long long steps,
+                           int n_slots, cudaStream_t s) {
+    if (n_recs <= 0 || steps <= 0 || v.n_words <= 0) return 0;
+    if (n_recs % RU != 0) return fail(MCB_ERR_ARG, "resident stream must be padded to %d", RU);
+    const size_t fixed = 2 * REC_CHUNK * sizeof(uint4) + 128;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    int max_smem = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    int block = g_tune.resident_block;
+    if (block > 256) block = 256;
+    if (block < 32) block = 32;
+    // shrink the CTA until the grid covers the SMs (few columns) ...
+    while (block > 32 && (v.n_words + block - 1) / block < sm_count()) block /= 2;
+    bool smem_state = false;
+    size_t smem = fixed;
+    if (g_tune.resident_smem) {
+        // ... and keep the whole slot file of the CTA's columns on chip when it fits
+        for (int b = block; b >= 32; b /= 2) {
+            size_t need = fixed + (size_t)n_slots * b * sizeof(uint64_t);
+            if (need <= (size_t)max_smem) { smem_state = true; smem = need; block = b; break; }
+        }
+    }
+    const long long grid = (v.n_words + block - 1) / block;
+    const bool tma = g_tune.resident_tma != 0;
+#define MCB_LR(T, S)                                                                       \
+    do {                                                                                   \
+        CUDA_TRY(cudaFuncSetAttribute(k_run_resident<T, S>,                                \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        k_run_resident<T, S><<<(unsigned)grid, block, smem, s>>>(recs, n_recs, v, steps, n_slots); \
+    } while (0)
+    if (tma && smem_state) MCB_LR(true, true);
+    else if (tma) MCB_LR(true, false);
+    else if (smem_state) MCB_LR(false, true);
+    else MCB_LR(false, false);
+#undef MCB_LR
+    LAUNCH_CHECK("k_run_resident");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: signatures / toggles.  One CTA per slot; lane words are folded with popc, the 64-bit
+// partial sums cross lanes by warp shuffle and cross warps through shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t warp_sum(uint64_t x) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+    return x;
+}
+
+__device__ __forceinline__ uint64_t block_sum(uint64_t x, uint64_t *sh) {
+    x = warp_sum(x);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[wid] = x;
+    __syncthreads();
+    uint64_t t = 0;
+    if (wid == 0) {
+        t = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0;
+        t = warp_sum(t);
+    }
+    return t;   // valid in warp 0
+}
+
+__global__ void __launch_bounds__(256)
+k_signature(const int *__restrict__ slots, int n, View v, long long col_offset,
+            uint64_t *popcount, uint64_t *checksum) {
+    __shared__ uint64_t sh[8];
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint64_t *r = row(v, (uint32_t)slots[i]);
+        uint64_t pc = 0, cs = 0;
+        for (long long j = threadIdx.x; j < v.n_words; j += blockDim.x) {
+            const uint64_t w = r[j];
+            pc += (uint64_t)__popcll(w);
+            cs += w * (2ull * (uint64_t)(col_offset + j) + 1ull);
+        }
+        pc = block_sum(pc, sh);
+        cs = block_sum(cs, sh);
+        if (threadIdx.x == 0) {
+            if (popcount) popcount[i] += pc;
+            if (checksum) checksum[i] += cs;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_toggle(const int *__restrict__ slots, int n, View v, uint64_t *shadow, long long shstride,
+         uint64_t *toggles) {
+    __shared__ uint64_t sh[8];
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint64_t *r = row(v, (uint32_t)slots[i]);
+        uint64_t *sd = shadow + (long long)i * shstride;
+        uint64_t t = 0;
+        for (long long j = threadIdx.x; j < v.n_words; j += blockDim.x) {
+            const uint64_t w = r[j];
+            t += (uint64_t)__popcll(w ^ sd[j]);
+            sd[j] = w;
+        }
+        t = block_sum(t, sh);
+        if (threadIdx.x == 0) toggles[i] += t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: stimulus, fills, pack / unpack
+// ------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    uint64_t z = x + 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void __launch_bounds__(256)
+k_stimulus(const int *__restrict__ slots, const int *__restrict__ streams, int n, View v,
+           long long col_offset, uint64_t seed) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= v.n_words) return;
+    for (int i = blockIdx.y; i < n; i += gridDim.y) {
+        const uint64_t s = (uint64_t)(uint32_t)streams[i];
+        row(v, (uint32_t)slots[i])[j] = splitmix64(seed ^ (s << 32) ^ (uint64_t)(col_offset + j));
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_fill_rows(const int *__restrict__ slots, const uint64_t *__restrict__ values, int n, View v) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= v.n_words) return;
+    for (int i = blockIdx.y; i < n; i += gridDim.y) row(v, (uint32_t)slots[i])[j] = values[i];
+}
+
+// 64 lanes (two per thread of a warp) -> one word per bit plane, by ballot
+__global__ void __launch_bounds__(256)
+k_pack(const uint64_t *__restrict__ values, int width, const int *__restrict__ slots, View v) {
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= v.n_words) return;
+    const uint64_t lo = values[warp * 64 + lane];
+    const uint64_t hi = values[warp * 64 + 32 + lane];
+    for (int b = 0; b < width; ++b) {
+        const uint32_t wl = __ballot_sync(0xffffffffu, (lo >> b) & 1ull);
+        const uint32_t wh = __ballot_sync(0xffffffffu, (hi >> b) & 1ull);
+        if (lane == 0) row(v, (uint32_t)slots[b])[warp] = ((uint64_t)wh << 32) | wl;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_unpack(uint64_t *__restrict__ values, int width, const int *__restrict__ slots, View v) {
+    const long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // lane index
+    if (l >= v.n_words * 64) return;
+    const long long j = l >> 6;
+    const int bit = (int)(l & 63);
+    uint64_t x = 0;
+    for (int b = 0; b < width; ++b) x |= ((row(v, (uint32_t)slots[b])[j] >> bit) & 1ull) << b;
+    values[l] = x;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------
+static int check_state(const mcb_state *st) {
+    if (!st) return fail(MCB_ERR_ARG, "state is NULL");
+    if (st->n_words < 0 || st->n_persist < 0 || st->n_slots < st->n_persist)
+        return fail(MCB_ERR_ARG, "bad state geometry");
+    if (st->n_persist > 0 && !st->d_persist) return fail(MCB_ERR_ARG, "d_persist is NULL");
+    if (st->n_slots > st->n_persist && !st->d_scratch) return fail(MCB_ERR_ARG, "d_scratch is NULL");
+    if ((st->persist_stride & 1) || (st->scratch_stride & 1))
+        return fail(MCB_ERR_ARG, "strides must be even (16-byte column pairs)");
+    if (((uintptr_t)st->d_persist & 15) || ((uintptr_t)st->d_scratch & 15))
+        return fail(MCB_ERR_ARG, "state planes must be 16-byte aligned");
+    if (st->n_persist > 0 && st->persist_stride < ((st->n_words + 1) & ~1ll))
+        return fail(MCB_ERR_ARG, "persist_stride smaller than the tile");
+    if (st->n_slots > st->n_persist && st->scratch_stride < ((st->n_words + 1) & ~1ll))
+        return fail(MCB_ERR_ARG, "scratch_stride smaller than the tile");
+    return 0;
+}
+
+extern "C" {
+
+int mcb_version(void) { return MCB_VERSION; }
+
+const char *mcb_last_error(void) { return g_err; }
+
+int64_t mcb_launch_count(int reset) {
+    long long v = reset ? g_launches.exchange(0) : g_launches.load();
+    return (int64_t)v;
+}
+
+int mcb_set_tuning(const char *key, int value) {
+    if (!key) return fail(MCB_ERR_ARG, "key is NULL");
+    int *p = nullptr;
+    if (!strcmp(key, "level_block")) p = &g_tune.level_block;
+    else if (!strcmp(key, "level_unroll")) p = &g_tune.level_unroll;
+    else if (!strcmp(key, "level_ctas_per_sm")) p = &g_tune.level_ctas_per_sm;
+    else if (!strcmp(key, "level_cache")) p = &g_tune.level_cache;
+    else if (!strcmp(key, "resident_block")) p = &g_tune.resident_block;
+    else if (!strcmp(key, "resident_tma")) p = &g_tune.resident_tma;
+    else if (!strcmp(key, "resident_smem")) p = &g_tune.resident_smem;
+    else if (!strcmp(key, "graph_min_steps")) p = &g_tune.graph_min_steps;
+    else return fail(MCB_ERR_ARG, "unknown tuning key %s", key);
+    int old = *p;
+    *p = value;
+    return old;
+}
+
+int mcb_device_info(int device, int *sms, int *cc_major, int *cc_minor, int64_t *total_mem,
+                    int64_t *l2_bytes) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(MCB_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(MCB_ERR_ARG, "device %d out of range", device);
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, device));
+    if (sms) *sms = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = (int64_t)p.totalGlobalMem;
+    if (l2_bytes) *l2_bytes = (int64_t)p.l2CacheSize;
+    if (p.major != 10)
+        return fail(MCB_ERR_ARCH, "device %d is sm_%d%d; this library carries sm_100a code only",
+                    device, p.major, p.minor);
+    return 0;
+}
+
+int mcb_eval_levels(const uint32_t *d_records, const int32_t *h_level_off, int level_begin,
+                    int level_end, const mcb_state *st, void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!d_records || !h_level_off || level_begin < 0 || level_end < level_begin)
+        return fail(MCB_ERR_ARG, "bad netlist arguments");
+    const View v = make_view(st);
+    const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
+    for (int l = level_begin; l < level_end; ++l) {
+        const int lo = h_level_off[l], hi = h_level_off[l + 1];
+        rc = launch_level(recs + lo, hi - lo, v, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !d_latch_records)) return fail(MCB_ERR_ARG, "bad latch list");
+    return launch_level(reinterpret_cast<const uint4 *>(d_latch_records), n, make_view(st),
+                        (cudaStream_t)stream);
+}
+
+int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
+            const mcb_state *st, int64_t steps, int mode, void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!d_records || !h_level_off || n_levels < 0 || steps < 0)
+        return fail(MCB_ERR_ARG, "bad run arguments");
+    if (steps == 0 || n_levels == 0) return 0;
+    cudaStream_t s = (cudaStream_t)stream;
+    const View v = make_view(st);
+    const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
+    if (mode == 0) {
+        for (int l = 0; l <= n_levels; ++l)
+            if (h_level_off[l] % RU)
+                return fail(MCB_ERR_ARG, "mode 0 needs every level padded to %d records", RU);
+        return launch_resident(recs, h_level_off[n_levels], v, steps, st->n_slots, s);
+    }
+    if (mode != 1) return fail(MCB_ERR_ARG, "unknown mode %d", mode);
+    if (steps < g_tune.graph_min_steps || s == nullptr) {
+        for (int64_t t = 0; t < steps; ++t) {
+            rc = mcb_eval_levels(d_records, h_level_off, 0, n_levels, st, stream);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+    // capture one step once, replay it `steps` times: no host round trip per level
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    const long long before = g_launches.load();
+    CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    rc = mcb_eval_levels(d_records, h_level_off, 0, n_levels, st, stream);
+    cudaError_t e = cudaStreamEndCapture(s, &graph);
+    const long long per_step = g_launches.load() - before;   // nodes captured, nothing ran yet
+    g_launches.store(before);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(MCB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&exec, graph, 0);
+    if (e != cudaSuccess) {
+        cudaGraphDestroy(graph);
+        return fail(MCB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+    for (int64_t t = 0; t < steps; ++t) {
+        e = cudaGraphLaunch(exec, s);
+        if (e != cudaSuccess) break;
+        g_launches.fetch_add(per_step, std::memory_order_relaxed);
+    }
+    cudaGraphExecDestroy(exec);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(MCB_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int mcb_signature(const int32_t *d_slots, int n, const mcb_state *st, int64_t col_offset,
+                  uint64_t *d_popcount, uint64_t *d_checksum, void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && !d_slots)) return fail(MCB_ERR_ARG, "bad slot list");
+    if (n == 0 || st->n_words == 0) return 0;
+    int grid = n < sm_count() * 8 ? n : sm_count() * 8;
+    k_signature<<<grid, 256, 0, (cudaStream_t)stream>>>(d_slots, n, make_view(st), col_offset,
+                                                         d_popcount, d_checksum);
+    LAUNCH_CHECK("k_signature");
+    return 0;
+}
+
+int mcb_toggle_accum(const int32_t *d_slots, int n, const mcb_state *st, uint64_t *d_shadow,
+                     int64_t shadow_stride, uint64_t *d_toggles, void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_slots || !d_shadow || !d_toggles)) || shadow_stride < st->n_words)
+        return fail(MCB_ERR_ARG, "bad toggle arguments");
+    if (n == 0 || st->n_words == 0) return 0;
+    int grid = n < sm_count() * 8 ? n : sm_count() * 8;
+    k_toggle<<<grid, 256, 0, (cudaStream_t)stream>>>(d_slots, n, make_view(st), d_shadow,
+                                                      shadow_stride, d_toggles);
+    LAUNCH_CHECK("k_toggle");
+    return 0;
+}
+
+static dim3 row_grid(long long n_words, int n) {
+    long long gx = (n_words + 255) / 256;
+    long long gy = n;
+    long long cap = (long long)sm_count() * 16 / (gx > 0 ? gx : 1);
+    if (cap < 1) cap = 1;
+    if (gy > cap) gy = cap;
+    if (gy > 65535) gy = 65535;
+    return dim3((unsigned)gx, (unsigned)gy, 1);
+}
+
+int mcb_stimulus(const int32_t *d_slots, const int32_t *d_streams, int n, const mcb_state *st,
+                 int64_t col_offset, uint64_t seed, void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_slots || !d_streams))) return fail(MCB_ERR_ARG, "bad stimulus list");
+    if (n == 0 || st->n_words == 0) return 0;
+    k_stimulus<<<row_grid(st->n_words, n), 256, 0, (cudaStream_t)stream>>>(
+        d_slots, d_streams, n, make_view(st), col_offset, seed);
+    LAUNCH_CHECK("k_stimulus");
+    return 0;
+}
+
+int mcb_fill_rows(const int32_t *d_slots, const uint64_t *d_values, int n, const mcb_state *st,
+                  void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_slots || !d_values))) return fail(MCB_ERR_ARG, "bad fill list");
+    if (n == 0 || st->n_words == 0) return 0;
+    k_fill_rows<<<row_grid(st->n_words, n), 256, 0, (cudaStream_t)stream>>>(d_slots, d_values, n,
+                                                                              make_view(st));
+    LAUNCH_CHECK("k_fill_rows");
+    return 0;
+}
+
+int mcb_pack(const uint64_t *d_values, int width, const int32_t *d_slots, const mcb_state *st,
+             void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (width < 1 || width > 64 || !d_values || !d_slots) return fail(MCB_ERR_ARG, "bad pack arguments");
+    if (st->n_words == 0) return 0;
+    const long long threads = st->n_words * 32;
+    k_pack<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_values, width, d_slots,
+                                                                                make_view(st));
+    LAUNCH_CHECK("k_pack");
+    return 0;
+}
+
+int mcb_unpack(uint64_t *d_values, int width, const int32_t *d_slots, const mcb_state *st,
+               void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (width < 1 || width > 64 || !d_values || !d_slots) return fail(MCB_ERR_ARG, "bad unpack arguments");
+    if (st->n_words == 0) return 0;
+    const long long threads = st->n_words * 64;
+    k_unpack<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_values, width, d_slots,
+                                                                                  make_view(st));
+    LAUNCH_CHECK("k_unpack");
+    return 0;
+}
+
+}  // extern "C"

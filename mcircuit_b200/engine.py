@@ -1,0 +1,400 @@
+"""B200Engine - the Executor of the drop-in simulation path.
+
+Mirrors the reference's ``JIT(root, burst_size, map_pins)`` (``core/simulator.py:174-297``):
+``get_pin_state``, ``set_pin_state``, ``step``, ``burst`` with the reference's semantics
+(pin paths, aliasing, ``burst`` = burst_size + 1 steps, constants visible before the first
+step, zero-initialised nets), and adds the multi-lane surface the reference does not have:
+``lanes=N`` independent stimulus instances evaluated at once, bit-sliced 64 per word.
+
+Documented deviations from the reference:
+  * values written with ``set_pin_state`` are masked to the pin width (reference writes 64
+    raw bits over an iW global, simulator.py:289-291);
+  * no ``out.txt`` side effect (simulator.py:266-267);
+  * ``Register`` follows the evident intent of simulator.py:115-127, which does not compile
+    in the reference;
+  * multi-driver nets, wire loops and width mismatches raise at build time.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import compiler
+from .compiler import PinNotObservable, Program
+from .runtime import MODE_LEVELS, MODE_RESIDENT, RESIDENT_UNROLL
+
+SEED = 0x6D63697263756974      # "mcircuit"
+_ALL = 0xFFFFFFFFFFFFFFFF
+_ALIGN_WORDS = 16              # rows start on 128-byte boundaries
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Executor:
+    """The reference's abstract interface (core/simulator.py:160-171)."""
+
+    def get_pin_state(self, pin):
+        raise NotImplementedError
+
+    def set_pin_state(self, pin, value):
+        raise NotImplementedError
+
+    def step(self):
+        raise NotImplementedError
+
+    def burst(self):
+        raise NotImplementedError
+
+
+def pad_levels(records: np.ndarray, level_off: np.ndarray, unroll: int = RESIDENT_UNROLL):
+    """Pad every level with NOP records to a multiple of ``unroll`` (resident kernel: a
+    batch of ``unroll`` records never straddles a level)."""
+    n_levels = len(level_off) - 1
+    sizes = np.diff(level_off).astype(np.int64)
+    padded = (sizes + unroll - 1) // unroll * unroll
+    new_off = np.zeros(n_levels + 1, dtype=np.int64)
+    np.cumsum(padded, out=new_off[1:])
+    out = np.zeros((int(new_off[-1]), 4), dtype=np.uint32)
+    if len(records):
+        # destination index of each original record
+        lvl = np.repeat(np.arange(n_levels), sizes)
+        dst = np.arange(len(records)) - level_off[:-1].astype(np.int64)[lvl] + new_off[:-1][lvl]
+        out[dst] = records
+    return out, new_off.astype(np.int32)
+
+
+class B200Engine(Executor):
+    def __init__(self, root, burst_size=500, map_pins=True, *, lanes=64, device=None,
+                 keep="auto", observe: Sequence[str] = (), tile_words: Optional[int] = None,
+                 mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
+                 memory_budget: Optional[int] = None):
+        if lanes < 1 or lanes % 64:
+            raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
+        if runtime is None:
+            from .runtime import CudaRuntime
+            runtime = CudaRuntime(device)           # raises when there is no B200 / no .so
+        self.rt = runtime
+        self.root = root
+        self.burst_size = int(burst_size)
+        self.map_pins = bool(map_pins)
+        self.lanes = int(lanes)
+        self.words = self.lanes // 64
+        self.lane_word_offset = int(lane_word_offset)   # global column of our column 0 (sharding)
+        self.stride = _round_up(self.words, _ALIGN_WORDS)
+        budget = memory_budget if memory_budget is not None else int(self.rt.free_bytes() * 0.80)
+
+        # ---- compile ------------------------------------------------------------------------
+        if program is None:
+            design = compiler.flatten(root, map_pins)
+            if keep == "auto":
+                keep = "all" if (design.n_signals * 3 // 2) * self.stride * 8 <= budget // 2 else "ports"
+            program = compiler.compile_design(design, keep=keep, observe=observe)
+        self.program = program
+        self.keep = keep
+        P, S = program.n_persist, program.n_scratch
+
+        # ---- execution mode -------------------------------------------------------------------
+        avg_level = program.n_ops / max(1, program.n_levels)
+        if mode == "auto":
+            # per-level launches pay off only when one level keeps the whole GPU busy
+            mode = "levels" if avg_level * min(self.words, 4096) >= (1 << 19) else "resident"
+        if mode not in ("levels", "resident"):
+            raise ValueError("mode must be 'auto', 'levels' or 'resident'")
+        self.mode = mode
+
+        # ---- tiling ------------------------------------------------------------------------------
+        persist_bytes = P * self.stride * 8
+        if tile_words is None:
+            if (P + S) * self.stride * 8 <= budget:
+                tile_words = self.words                      # everything resident, one tile
+            else:
+                room = max(budget - persist_bytes, 0)
+                tile_words = max(_ALIGN_WORDS, min(4096, (room // max(1, S * 8)) // _ALIGN_WORDS * _ALIGN_WORDS))
+        tile_words = int(min(tile_words, self.words))
+        if tile_words < self.words:
+            tile_words = max(_ALIGN_WORDS, tile_words // _ALIGN_WORDS * _ALIGN_WORDS)
+        self.tile_words = tile_words
+        self.n_tiles = (self.words + tile_words - 1) // tile_words
+        if persist_bytes + S * _round_up(tile_words, _ALIGN_WORDS) * 8 > budget:
+            raise MemoryError(
+                "state does not fit: %d persistent slots x %d words + %d scratch slots x %d words"
+                % (P, self.stride, S, tile_words))
+
+        # ---- buffers (torch owns them) ---------------------------------------------------------------
+        if self.n_tiles == 1:
+            # one plane: scratch rows follow the persistent rows with the same stride
+            self._plane = self.rt.zeros_words((P + S) * self.stride + _ALIGN_WORDS)
+            self._scratch = None
+            self.scratch_stride = self.stride
+        else:
+            self._plane = self.rt.zeros_words(P * self.stride + _ALIGN_WORDS)
+            self.scratch_stride = _round_up(tile_words, _ALIGN_WORDS)
+            self._scratch = self.rt.zeros_words(S * self.scratch_stride + _ALIGN_WORDS)
+        self._d_records = self.rt.to_device(program.records)
+        self._h_level_off = np.ascontiguousarray(program.level_off, dtype=np.int32)
+        self._resident = None      # (d_records_padded, h_level_off_padded), built on first use
+        self._whole = self._state_for(0, self.words, whole=True)
+        self._slot_cache: Dict[str, object] = {}
+        self.steps_done = 0
+        self._toggle = None
+
+        for base, width, value in program.constants:           # simulator.py:275-276
+            self._poke_signals(base, width, int(value))
+
+    # ------------------------------------------------------------------------------------------
+    # state views
+    # ------------------------------------------------------------------------------------------
+    def _state_for(self, col0, n_words, whole=False):
+        P, S = self.program.n_persist, self.program.n_scratch
+        if self.n_tiles == 1:
+            return self.rt.make_state(self._plane, self.stride, self._plane, self.stride, P, P + S,
+                                      n_words, col_offset=col0,
+                                      scratch_col_offset=P * self.stride + col0)
+        if whole:
+            # persistent rows only (pin access, stimulus, signatures)
+            return self.rt.make_state(self._plane, self.stride, None, 0, P, P, n_words, col_offset=col0)
+        return self.rt.make_state(self._plane, self.stride, self._scratch, self.scratch_stride,
+                                  P, P + S, n_words, col_offset=col0)
+
+    def _tiles(self):
+        for t in range(self.n_tiles):
+            c0 = t * self.tile_words
+            yield c0, min(self.tile_words, self.words - c0)
+
+    # ------------------------------------------------------------------------------------------
+    # Executor interface (core/simulator.py:285-297)
+    # ------------------------------------------------------------------------------------------
+    def step(self):
+        self.run(1)
+
+    def burst(self):
+        # the reference's loop tests the pre-decrement counter: burst_size + 1 passes (Q1)
+        self.run(self.burst_size + 1)
+
+    def tick(self):
+        """One full clock period of a ``Clock`` = two steps (it toggles every step)."""
+        self.run(2)
+
+    def run(self, steps: int):
+        """``steps`` evaluation passes with all state resident on the device."""
+        steps = int(steps)
+        if steps <= 0 or self.program.n_ops == 0:
+            self.steps_done += max(steps, 0)
+            return
+        if self._toggle is not None:
+            for _ in range(steps):
+                self._run_raw(1)
+                self._toggle_sample()
+        else:
+            self._run_raw(steps)
+        self.steps_done += steps
+
+    def _run_raw(self, steps):
+        if self.mode == "resident":
+            if self._resident is None:
+                rec, off = pad_levels(self.program.records, self.program.level_off)
+                self._resident = (self.rt.to_device(rec), off)
+            d_rec, off = self._resident
+            for c0, n in self._tiles():
+                self.rt.run(d_rec, off, self.program.n_levels, self._state_for(c0, n), steps, MODE_RESIDENT)
+        else:
+            for c0, n in self._tiles():
+                self.rt.run(self._d_records, self._h_level_off, self.program.n_levels,
+                            self._state_for(c0, n), steps, MODE_LEVELS)
+
+    # ---- pins --------------------------------------------------------------------------------------
+    def _slots_of(self, pin: str, need_value=True):
+        key = (pin, need_value)
+        hit = self._slot_cache.get(key)
+        if hit is None:
+            base, width = self.program.pin_signals(pin)      # KeyError on unknown pin (Q10)
+            slots = self.program.pin_slots(pin, need_value=need_value)
+            shadows = [self.program.sig_shadow.get(base + b, -1) for b in range(width)]
+            hit = (base, width, slots, shadows)
+            self._slot_cache[key] = hit
+        return hit
+
+    def _poke_signals(self, base, width, value: int):
+        slots, vals = [], []
+        for b in range(width):
+            s = int(self.program.sig_slot[base + b])
+            if s < 0 or s >= self.program.n_persist:
+                continue                 # recycled net: a poke could not survive anyway
+            word = _ALL if (value >> b) & 1 else 0
+            slots.append(s)
+            vals.append(word)
+            sh = self.program.sig_shadow.get(base + b)
+            if sh is not None:
+                slots.append(sh)
+                vals.append(word)
+        if slots:
+            self.rt.fill_rows(self.rt.to_device(np.asarray(slots, dtype=np.int32)),
+                              self.rt.to_device(np.asarray(vals, dtype=np.uint64)), len(slots), self._whole)
+
+    def set_pin_state(self, pin, value):
+        """Scalar: every lane gets ``value`` (masked to the pin width).  Array of ``lanes``
+        uint64: one value per lane."""
+        base, width, slots, shadows = self._slots_of(pin, need_value=False)
+        if np.isscalar(value) or isinstance(value, int):
+            self._poke_signals(base, width, int(value) & ((1 << width) - 1))
+            return
+        v = np.ascontiguousarray(np.asarray(value).astype(np.uint64, copy=False))
+        if v.shape != (self.lanes,):
+            raise ValueError("expected %d lane values, got shape %s" % (self.lanes, v.shape))
+        d_vals = self.rt.to_device(v)
+        for group in (slots, shadows):
+            if any(s < 0 or s >= self.program.n_persist for s in group):
+                if group is slots:
+                    raise PinNotObservable("%s is not retained; cannot drive it per lane" % pin)
+                continue
+            self.rt.pack(d_vals, width, self.rt.to_device(np.asarray(group, dtype=np.int32)), self._whole)
+
+    def get_pin_state(self, pin, lanes=False):
+        """Scalar form returns lane 0 as a Python int (the reference's single instance);
+        ``lanes=True`` returns all lanes as uint64[lanes]."""
+        base, width, slots, _ = self._slots_of(pin)
+        if lanes:
+            d_vals = self.rt.empty_words(self.lanes)
+            self.rt.unpack(d_vals, width, self.rt.to_device(np.asarray(slots, dtype=np.int32)), self._whole)
+            return self.rt.to_host_u64(d_vals)
+        idx = np.asarray(slots, dtype=np.int64) * self.stride
+        words = self.rt.to_host_u64(self._plane[self.rt.to_device(idx)])
+        value = 0
+        for b in range(width):
+            value |= (int(words[b]) & 1) << b
+        return value
+
+    # bit-plane access: rows of the slot-major state, no transposition
+    def set_pin_planes(self, pin, planes):
+        """planes: uint64[width, words] - bit b of every lane word, already bit-sliced."""
+        base, width, slots, shadows = self._slots_of(pin, need_value=False)
+        p = np.ascontiguousarray(np.asarray(planes, dtype=np.uint64)).reshape(width, self.words)
+        d = self.rt.to_device(p)
+        for group in (slots, shadows):
+            for b, s in enumerate(group):
+                if 0 <= s < self.program.n_persist:
+                    self._plane[s * self.stride: s * self.stride + self.words] = d[b]
+
+    def get_pin_planes(self, pin) -> np.ndarray:
+        base, width, slots, _ = self._slots_of(pin)
+        out = np.empty((width, self.words), dtype=np.uint64)
+        for b, s in enumerate(slots):
+            out[b] = self.rt.to_host_u64(self._plane[s * self.stride: s * self.stride + self.words])
+        return out
+
+    # ---- stimulus / signatures --------------------------------------------------------------------------
+    def input_pins(self) -> List[str]:
+        """Root-level IN ports, in child order."""
+        d = self.program.design
+        out = []
+        for name, child in d.top.children.items():
+            if isinstance(child, int):
+                desc = d.leaf_desc[child]
+                if type(desc).__name__ == "ExposedPin" and desc.direction == 0:
+                    out.append("/%s/pin" % name)
+        return out
+
+    def output_pins(self) -> List[str]:
+        d = self.program.design
+        out = []
+        for name, child in d.top.children.items():
+            if isinstance(child, int):
+                desc = d.leaf_desc[child]
+                if type(desc).__name__ == "ExposedPin" and desc.direction == 1:
+                    out.append("/%s/pin" % name)
+        return out
+
+    def _flat_slots(self, pins: Sequence[str]) -> List[int]:
+        out: List[int] = []
+        for p in pins:
+            out.extend(self._slots_of(p)[2])
+        return out
+
+    def randomize_inputs(self, pins: Optional[Sequence[str]] = None, seed: int = SEED):
+        """Counter-based stimulus straight into the bit-sliced layout (K5):
+        word(stream s, column j) = splitmix64(seed ^ (s << 32) ^ (lane_word_offset + j)),
+        stream s = running bit index over ``pins``.  Regenerable on any host or GPU."""
+        pins = self.input_pins() if pins is None else list(pins)
+        slots, streams = [], []
+        s = 0
+        for p in pins:
+            base, width, sl, sh = self._slots_of(p, need_value=False)
+            for b in range(width):
+                slots.append(sl[b])
+                streams.append(s)
+                if sh[b] >= 0:
+                    slots.append(sh[b])
+                    streams.append(s)
+                s += 1
+        if slots:
+            self.rt.stimulus(self.rt.to_device(np.asarray(slots, dtype=np.int32)),
+                             self.rt.to_device(np.asarray(streams, dtype=np.int32)), len(slots),
+                             self._whole, self.lane_word_offset, seed)
+        return s
+
+    def signature(self, pins: Optional[Sequence[str]] = None):
+        """(popcount[n_bits], checksum[n_bits]) over all lanes of every bit of ``pins``
+        (default: root OUT ports).  Sums - shards combine with an all-reduce SUM (K4)."""
+        pins = self.output_pins() if pins is None else list(pins)
+        slots = self._flat_slots(pins)
+        n = len(slots)
+        d_pc, d_cs = self.signature_device(slots)
+        if n == 0:
+            return np.zeros(0, np.uint64), np.zeros(0, np.uint64)
+        return self.rt.to_host_u64(d_pc), self.rt.to_host_u64(d_cs)
+
+    def signature_device(self, slots: Sequence[int]):
+        n = len(slots)
+        d_pc = self.rt.zeros_words(max(n, 1))
+        d_cs = self.rt.zeros_words(max(n, 1))
+        if n:
+            self.rt.signature(self.rt.to_device(np.asarray(slots, dtype=np.int32)), n, self._whole,
+                              self.lane_word_offset, d_pc, d_cs)
+        return d_pc[:n], d_cs[:n]
+
+    # ---- toggle coverage ---------------------------------------------------------------------------------
+    def enable_toggle_counts(self, pins: Sequence[str]):
+        """Count, per bit of ``pins``, how many lane bits change from one step to the next."""
+        slots = self._flat_slots(pins)
+        n = len(slots)
+        self._toggle = {
+            "pins": list(pins), "n": n,
+            "d_slots": self.rt.to_device(np.asarray(slots, dtype=np.int32)),
+            "shadow": self.rt.zeros_words(max(1, n * self.stride)),
+            "counts": self.rt.zeros_words(max(1, n)),
+        }
+        # prime the shadow with the current values so the first step counts real toggles
+        self._toggle_sample()
+        self._toggle["counts"][:] = 0
+
+    def _toggle_sample(self):
+        t = self._toggle
+        if t["n"]:
+            self.rt.toggle_accum(t["d_slots"], t["n"], self._whole, t["shadow"], self.stride, t["counts"])
+
+    def toggle_counts(self) -> np.ndarray:
+        if self._toggle is None:
+            raise RuntimeError("enable_toggle_counts() first")
+        return self.rt.to_host_u64(self._toggle["counts"][: self._toggle["n"]])
+
+    def toggle_counts_device(self):
+        return self._toggle["counts"][: self._toggle["n"]]
+
+    # ---- accounting ----------------------------------------------------------------------------------------
+    def synchronize(self):
+        self.rt.synchronize()
+
+    @property
+    def gates_per_step(self) -> int:
+        return self.program.n_gates
+
+    def gate_evals(self, steps=1) -> int:
+        """lanes x gates x steps (BASELINE.json metric)."""
+        return self.lanes * self.program.n_gates * int(steps)
+
+    def algorithmic_bytes(self, steps=1) -> int:
+        """8 B per fan-in word read + 8 B per output word written, per record."""
+        return self.program.gate_words_bytes * self.words * int(steps)

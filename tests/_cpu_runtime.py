@@ -1,0 +1,216 @@
+"""TEST DOUBLE - a numpy stand-in for ``mcircuit_b200.runtime.CudaRuntime``.
+
+Lives under tests/ and is only ever injected by tests (``B200Engine(..., runtime=CpuRuntime())``)
+so that the host logic - compiler output, tiling, pin access, sharding, the gloo multi-process
+path - can be exercised without a GPU.  The product never imports it and has no CPU path.
+It interprets the *compiled* program (records, levels, slots) the way the kernels do, which
+also makes it the checker of the compiler against oracle/restate.py.
+"""
+import numpy as np
+
+U64 = np.uint64
+ALL = U64(0xFFFFFFFFFFFFFFFF)
+
+
+class _State:
+    def __init__(self, persist, pstride, pcol, scratch, sstride, scol, n_persist, n_slots, n_words):
+        self.persist, self.pstride, self.pcol = persist, pstride, pcol
+        self.scratch, self.sstride, self.scol = scratch, sstride, scol
+        self.n_persist, self.n_slots, self.n_words = n_persist, n_slots, n_words
+
+    def rows(self, slots):
+        """index array [len(slots), n_words] into the right plane, and which plane"""
+        slots = np.asarray(slots, dtype=np.int64)
+        cols = np.arange(self.n_words, dtype=np.int64)
+        return slots, cols
+
+    def read(self, slots):
+        slots = np.asarray(slots, dtype=np.int64)
+        out = np.empty((len(slots), self.n_words), dtype=U64)
+        cols = np.arange(self.n_words, dtype=np.int64)
+        p = slots < self.n_persist
+        if p.any():
+            idx = slots[p][:, None] * self.pstride + self.pcol + cols[None, :]
+            out[p] = self.persist[idx]
+        if (~p).any():
+            idx = (slots[~p] - self.n_persist)[:, None] * self.sstride + self.scol + cols[None, :]
+            out[~p] = self.scratch[idx]
+        return out
+
+    def write(self, slots, values):
+        slots = np.asarray(slots, dtype=np.int64)
+        cols = np.arange(self.n_words, dtype=np.int64)
+        p = slots < self.n_persist
+        if p.any():
+            idx = slots[p][:, None] * self.pstride + self.pcol + cols[None, :]
+            self.persist[idx] = values[p]
+        if (~p).any():
+            idx = (slots[~p] - self.n_persist)[:, None] * self.sstride + self.scol + cols[None, :]
+            self.scratch[idx] = values[~p]
+
+
+def _apply(op, a, b, c):
+    base = op & 0x7F
+    if base == 1:
+        r = a
+    elif base == 2:
+        r = a & b
+    elif base == 3:
+        r = a | b
+    elif base == 4:
+        r = a ^ b
+    elif base == 5:
+        r = a & ~b
+    elif base == 6:
+        r = (a & b) | (~a & c)
+    elif base == 7:
+        r = a & b & c
+    elif base == 8:
+        r = a | b | c
+    elif base == 9:
+        r = a ^ b ^ c
+    elif base == 10:
+        r = (a & b) | (a & c) | (b & c)
+    else:
+        raise ValueError("bad opcode %d" % op)
+    return ~r if op & 0x80 else r
+
+
+def splitmix64(x):
+    x = np.asarray(x, dtype=U64)
+    with np.errstate(over="ignore"):
+        z = x + U64(0x9E3779B97F4A7C15)
+        z = (z ^ (z >> U64(30))) * U64(0xBF58476D1CE4E5B9)
+        z = (z ^ (z >> U64(27))) * U64(0x94D049BB133111EB)
+        return z ^ (z >> U64(31))
+
+
+class CpuRuntime:
+    name = "cpu-test-double"
+
+    def __init__(self, memory=1 << 30):
+        self._memory = memory
+        self._launches = 0
+        self.sm_count = 148
+        self.l2_bytes = 126 << 20
+        self.total_mem = memory
+
+    def free_bytes(self):
+        return self._memory
+
+    def zeros_words(self, n):
+        return np.zeros(int(n), dtype=U64)
+
+    def empty_words(self, n):
+        return np.zeros(int(n), dtype=U64)
+
+    def to_device(self, a):
+        return np.array(a, copy=True)
+
+    def to_host_u64(self, a):
+        return np.array(a, copy=True).view(U64)
+
+    def synchronize(self):
+        pass
+
+    def make_state(self, persist, persist_stride, scratch, scratch_stride, n_persist, n_slots,
+                   n_words, col_offset=0, scratch_col_offset=0):
+        return _State(persist, persist_stride, col_offset, scratch, scratch_stride,
+                      scratch_col_offset, n_persist, n_slots, n_words)
+
+    # ---- program execution: level by level, all records of a level "at once" -----------------
+    def _level(self, recs, st):
+        if len(recs) == 0:
+            return
+        self._launches += 1
+        op = recs[:, 0] & 0xFF
+        live = (op & 0x7F) != 0
+        recs, op = recs[live], op[live]
+        if len(recs) == 0:
+            return
+        a = st.read(recs[:, 1])
+        b = st.read(recs[:, 2])
+        c = st.read(recs[:, 0] >> 8)
+        out = np.empty_like(a)
+        for code in np.unique(op):
+            m = op == code
+            out[m] = _apply(int(code), a[m], b[m], c[m])
+        st.write(recs[:, 3], out)
+
+    def eval_levels(self, d_records, h_level_off, lo, hi, st):
+        for lv in range(lo, hi):
+            self._level(d_records[h_level_off[lv]:h_level_off[lv + 1]].astype(np.int64), st)
+
+    def latch(self, d_records, n, st):
+        self._level(d_records[:n].astype(np.int64), st)
+
+    def run(self, d_records, h_level_off, n_levels, st, steps, mode):
+        if mode == 0:
+            assert all(int(x) % 4 == 0 for x in h_level_off), "resident stream must be padded"
+            # batches of 4 records, loads before stores - exactly the kernel's hazard model
+            recs = d_records.astype(np.int64)
+            for _ in range(int(steps)):
+                for i in range(0, int(h_level_off[n_levels]), 4):
+                    self._level(recs[i:i + 4], st)
+        else:
+            for _ in range(int(steps)):
+                self.eval_levels(d_records, h_level_off, 0, n_levels, st)
+
+    # ---- K4 / K5 ---------------------------------------------------------------------------------
+    def signature(self, d_slots, n, st, col_offset, d_popcount, d_checksum):
+        rows = st.read(d_slots[:n])
+        cols = np.arange(st.n_words, dtype=U64) + U64(col_offset)
+        with np.errstate(over="ignore"):
+            if d_popcount is not None:
+                pc = np.array([sum(bin(int(w)).count("1") for w in r) for r in rows], dtype=U64)
+                d_popcount[:n] += pc
+            if d_checksum is not None:
+                d_checksum[:n] += (rows * (U64(2) * cols + U64(1))[None, :]).sum(axis=1, dtype=U64)
+        self._launches += 1
+
+    def toggle_accum(self, d_slots, n, st, d_shadow, shadow_stride, d_toggles):
+        rows = st.read(d_slots[:n])
+        for i in range(n):
+            sh = d_shadow[i * shadow_stride: i * shadow_stride + st.n_words]
+            d_toggles[i] += U64(sum(bin(int(w)).count("1") for w in (rows[i] ^ sh)))
+            sh[:] = rows[i]
+        self._launches += 1
+
+    def stimulus(self, d_slots, d_streams, n, st, col_offset, seed):
+        cols = np.arange(st.n_words, dtype=U64) + U64(col_offset)
+        s = np.asarray(d_streams[:n]).astype(U64)
+        vals = splitmix64(U64(seed) ^ (s[:, None] << U64(32)) ^ cols[None, :])
+        st.write(d_slots[:n], vals)
+        self._launches += 1
+
+    def fill_rows(self, d_slots, d_values, n, st):
+        vals = np.repeat(np.asarray(d_values[:n]).view(U64)[:, None], st.n_words, axis=1)
+        st.write(d_slots[:n], vals)
+        self._launches += 1
+
+    def pack(self, d_values, width, d_slots, st):
+        v = np.asarray(d_values).view(U64)[: st.n_words * 64].reshape(st.n_words, 64)
+        weights = U64(1) << np.arange(64, dtype=U64)
+        planes = np.empty((width, st.n_words), dtype=U64)
+        for b in range(width):
+            planes[b] = (((v >> U64(b)) & U64(1)) * weights).sum(axis=1, dtype=U64)
+        st.write(d_slots[:width], planes)
+        self._launches += 1
+
+    def unpack(self, d_values, width, d_slots, st):
+        planes = st.read(d_slots[:width])
+        shifts = np.arange(64, dtype=U64)
+        out = np.zeros(st.n_words * 64, dtype=U64)
+        for b in range(width):
+            out |= (((planes[b][:, None] >> shifts[None, :]) & U64(1)).reshape(-1)) << U64(b)
+        d_values[: st.n_words * 64] = out
+        self._launches += 1
+
+    def set_tuning(self, key, value):
+        return 0
+
+    def launch_count(self, reset=False):
+        n = self._launches
+        if reset:
+            self._launches = 0
+        return n
