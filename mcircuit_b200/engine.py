@@ -347,13 +347,66 @@ class B200Engine(Executor):
         return self.rt.to_host_u64(d_pc), self.rt.to_host_u64(d_cs)
 
     def signature_device(self, slots: Sequence[int]):
+        plan = self.signature_plan(slots=slots)
+        self.signature_run(plan)
+        n = plan["n"]
+        return plan["buf"][:n], plan["buf"][plan["half"]:plan["half"] + n]
+
+    def signature_plan(self, pins: Optional[Sequence[str]] = None, slots: Optional[Sequence[int]] = None):
+        """Pre-stage the slot list and one device buffer [popcounts | checksums] so that a
+        signature per step costs one memset + one kernel (+ one all-reduce when sharded)."""
+        if slots is None:
+            slots = self._flat_slots(self.output_pins() if pins is None else list(pins))
         n = len(slots)
-        d_pc = self.rt.zeros_words(max(n, 1))
-        d_cs = self.rt.zeros_words(max(n, 1))
+        half = max(n, 1)
+        return {"n": n, "half": half, "buf": self.rt.zeros_words(2 * half),
+                "d_slots": self.rt.to_device(np.asarray(list(slots) or [0], dtype=np.int32))}
+
+    def signature_run(self, plan):
+        buf, n, half = plan["buf"], plan["n"], plan["half"]
+        buf[:] = 0
         if n:
-            self.rt.signature(self.rt.to_device(np.asarray(slots, dtype=np.int32)), n, self._whole,
-                              self.lane_word_offset, d_pc, d_cs)
-        return d_pc[:n], d_cs[:n]
+            self.rt.signature(plan["d_slots"], n, self._whole, self.lane_word_offset,
+                              buf[:half], buf[half:])
+        return buf
+
+    # ---- bulk host <-> device I/O of whole pins (bit planes), coalescing adjacent rows --------
+    def _row_runs(self, slots: Sequence[int]):
+        runs, start, prev = [], None, None
+        for k, s in enumerate(slots):
+            if start is None:
+                start, first_k = s, k
+            elif s != prev + 1:
+                runs.append((start, prev - start + 1, first_k))
+                start, first_k = s, k
+            prev = s
+        if start is not None:
+            runs.append((start, prev - start + 1, first_k))
+        return runs
+
+    def io_plan(self, pins: Sequence[str]):
+        """Slots of all bits of ``pins`` (in order) + maximal runs of adjacent rows."""
+        slots = []
+        for p in pins:
+            slots.extend(self._slots_of(p, need_value=False)[2])
+        if any(s < 0 or s >= self.program.n_persist for s in slots):
+            raise PinNotObservable("bulk I/O needs retained pins")
+        return {"slots": slots, "runs": self._row_runs(slots), "n": len(slots)}
+
+    def rows_view(self, first_slot, count):
+        """Device view [count, words] of adjacent persistent rows (contiguous when
+        stride == words)."""
+        flat = self._plane[first_slot * self.stride:(first_slot + count) * self.stride]
+        return flat.reshape(count, self.stride)[:, :self.words]
+
+    def upload_rows(self, plan, host_rows, non_blocking=True):
+        """host_rows: [n, words] int64/uint64 tensor or array (pinned for async)."""
+        for first, count, k in plan["runs"]:
+            self.rows_view(first, count).copy_(host_rows[k:k + count], non_blocking=non_blocking)
+
+    def download_rows(self, plan, host_rows, non_blocking=True):
+        for first, count, k in plan["runs"]:
+            host_rows[k:k + count].copy_(self.rows_view(first, count), non_blocking=non_blocking)
 
     # ---- toggle coverage ---------------------------------------------------------------------------------
     def enable_toggle_counts(self, pins: Sequence[str]):

@@ -1,0 +1,258 @@
+"""not-gpu: the netlist compiler + engine host logic, executed by the numpy test double
+(tests/_cpu_runtime.py) and checked against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+import mcircuit_b200.core.descriptors as MD
+from _cpu_runtime import CpuRuntime
+from _helpers import (build, compare_engine_to_oracle, golden, lane_trick_planes,
+                      run_register_case, run_trace_case)
+from mcircuit_b200 import circuits, compiler
+from mcircuit_b200.engine import B200Engine, pad_levels
+
+TRACES = golden("traces.json")
+
+
+def engine_factory(mode="resident", keep="all", map_pins=True, **kw):
+    def make(root, burst_size, lanes=64):
+        return B200Engine(root, burst_size, map_pins, lanes=lanes, runtime=CpuRuntime(),
+                          mode=mode, keep=keep, **kw)
+    return make
+
+
+@pytest.mark.parametrize("case", TRACES, ids=[c["name"] for c in TRACES])
+@pytest.mark.parametrize("mode,keep,map_pins", [("resident", "all", True), ("levels", "ports", True),
+                                                ("levels", "all", False)])
+def test_engine_traces(case, mode, keep, map_pins):
+    run_trace_case(case, engine_factory(mode, keep, map_pins), skip_unobservable=(keep == "ports"))
+
+
+@pytest.mark.parametrize("case", golden("register_intent.json"), ids=lambda c: c["name"])
+def test_engine_register_intent(case):
+    run_register_case(case, engine_factory("levels"))
+
+
+@pytest.mark.parametrize("case", golden("adder.json"), ids=lambda c: c["name"])
+def test_engine_adder(case):
+    w = case["width"]
+    top = MD.Composite()
+    top.add_child("add", MD.Adder(w))
+    vecs = case["vectors"]
+    lanes = (len(vecs) + 63) // 64 * 64
+    pad = lanes - len(vecs)
+    eng = B200Engine(top, 1, True, lanes=lanes, runtime=CpuRuntime())
+    col = lambda k: np.array([v[k] for v in vecs] + [0] * pad, dtype=np.uint64)
+    eng.set_pin_state("/add/a", col(0))
+    eng.set_pin_state("/add/b", col(1))
+    eng.set_pin_state("/add/cin", col(2))
+    eng.step()
+    s = eng.get_pin_state("/add/sum", lanes=True)
+    c = eng.get_pin_state("/add/cout", lanes=True)
+    for i, (ws, wc) in enumerate(case["results"]):
+        assert (int(s[i]), int(c[i])) == (ws, wc), (w, vecs[i])
+
+
+@pytest.mark.parametrize("case", golden("lane_trick.json"), ids=lambda c: c["name"])
+@pytest.mark.parametrize("tile_words", [None, 16])
+def test_engine_lane_trick(case, tile_words):
+    ins, outs = lane_trick_planes(case)
+    nw = case["n_words"]
+    # replicate the words so that several tiles exist when tiling is forced
+    reps = 1 if tile_words is None else 5
+    eng = B200Engine(build(case), 1, True, lanes=64 * nw * reps, runtime=CpuRuntime(), mode="levels",
+                     keep="ports", tile_words=tile_words)
+    if tile_words is not None:
+        assert eng.n_tiles > 1
+    for p, words in ins.items():
+        eng.set_pin_planes(p, np.tile(words, reps)[None, :])
+    eng.step()
+    for p, words in outs.items():
+        assert np.array_equal(eng.get_pin_planes(p)[0], np.tile(words, reps)), p
+
+
+@pytest.mark.parametrize("seed", range(100, 130))
+def test_engine_vs_oracle_all_lanes(seed):
+    root, probes = circuits.random_circuit(MD, seed, n_nodes=22)
+    d = compiler.flatten(root)
+    lane_inputs = [("/in0/pin", d.pin_width[d.find_pin("/in0/pin")]),
+                   ("/in1/pin", d.pin_width[d.find_pin("/in1/pin")])]
+    mode = ("resident", "levels")[seed % 2]
+    compare_engine_to_oracle(lambda M: circuits.random_circuit(M, seed, n_nodes=22),
+                             lambda r, bs, lanes: engine_factory(mode)(r, bs, lanes),
+                             lanes=128, steps=6, probes=probes, lane_inputs=lane_inputs, seed=seed)
+
+
+def test_lfsr_pipeline_small_vs_oracle():
+    probes = [f"/tap{n}/pin" for n in range(3)] + ["/pipe_out/pin"] + [f"/l1_q{b}/out" for b in range(8)]
+    pokes = [(f"/l{n}_q{b}/out", (n + b) & 1) for n in range(3) for b in range(8)]
+    for mode in ("resident", "levels"):
+        compare_engine_to_oracle(lambda M: circuits.lfsr_pipeline(M, 3, 8, 10, taps=(7, 5, 1, 0)),
+                                 lambda r, bs, lanes: engine_factory(mode)(r, bs, lanes),
+                                 lanes=64, steps=40, probes=probes, pokes=pokes)
+
+
+def test_burst_and_run_and_tick():
+    eng = engine_factory()(circuits.counter_circuit(MD), 501)
+    for _ in range(8):
+        eng.step()
+    eng.burst()
+    assert eng.steps_done == 8 + 502
+    assert (eng.get_pin_state("/clk/out"), eng.get_pin_state("/r/out"), eng.get_pin_state("/r/prevclock")) == (0, 1, 0)
+    eng.tick()
+    assert eng.steps_done == 8 + 502 + 2
+
+
+def test_constants_visible_before_first_step_and_masking():
+    top = MD.Composite()
+    top.add_child("c", MD.Constant(5, 0b10110))
+    top.add_child("n", MD.Not(5))
+    top.connect("c", "out", "n", "in")
+    eng = engine_factory()(top, 1)
+    assert eng.get_pin_state("/c/out") == 0b10110
+    assert eng.get_pin_state("/n/in") == 0b10110          # aliases its source (Q7)
+    eng.step()
+    assert eng.get_pin_state("/n/out") == 0b01001
+    eng.set_pin_state("/n/in", 0xFFFF)                     # written through to the source, masked (Q9)
+    assert eng.get_pin_state("/c/out") == 0b11111
+
+
+def test_unknown_pin_raises_keyerror():
+    eng = engine_factory()(circuits.counter_circuit(MD), 1)
+    for bad in ("/nope/out", "/clk/nope", "clk/out", "/clk", "/clk/out/x"):
+        with pytest.raises(KeyError):
+            eng.get_pin_state(bad)
+    with pytest.raises(KeyError):
+        eng.set_pin_state("/r/nope", 1)
+
+
+def test_build_time_validation():
+    top = MD.Composite()
+    top.add_child("a", MD.Not(8))
+    top.add_child("b", MD.Not(4))
+    top.connect("a", "out", "b", "in")
+    with pytest.raises(compiler.CircuitError):
+        compiler.compile_circuit(top)
+    top = MD.Composite()
+    top.add_child("a", MD.Not())
+    top.add_child("b", MD.Not())
+    top.add_child("c", MD.Not())
+    top.connect("a", "out", "c", "in")
+    top.connect("b", "out", "c", "in")
+    with pytest.raises(compiler.CircuitError):
+        compiler.compile_circuit(top)
+    top = MD.Composite()
+    top.add_child("a", MD.Not())
+    top.add_child("b", MD.Not())
+    top.connect("a", "out", "b", "nope")
+    with pytest.raises(KeyError):
+        compiler.compile_circuit(top)
+    top = MD.Composite()
+    top.add_child("g", MD.Gate(MD.Gate.AND, 1, 0))
+    with pytest.raises(compiler.CircuitError):
+        compiler.compile_circuit(top)
+
+
+def test_ports_mode_recycles_and_reports_unobservable():
+    root = circuits.random_dag(MD, n_gates=600, depth=12, n_inputs=16, seed=5)
+    full = compiler.compile_circuit(root, keep="all")
+    lean = compiler.compile_circuit(root, keep="ports")
+    assert full.n_scratch == 0 and lean.n_scratch > 0
+    assert lean.n_persist == 16 + 50                       # inputs + last-level outputs
+    assert lean.n_slots < full.n_slots / 2
+    assert lean.n_gates == full.n_gates == 600
+    assert lean.n_levels == 12 and not lean.has_latch
+    assert lean.gate_words_bytes == 600 * 24               # 24 B per 2-input gate word
+    eng = B200Engine(root, 1, True, lanes=64, runtime=CpuRuntime(), keep="ports")
+    eng.step()
+    with pytest.raises(compiler.PinNotObservable):
+        eng.get_pin_state("/g3_7/out")
+    eng2 = B200Engine(root, 1, True, lanes=64, runtime=CpuRuntime(), keep="ports", observe=["/g3_7/out"])
+    eng2.step()
+    eng2.get_pin_state("/g3_7/out")
+
+
+def test_levelization_invariants():
+    """Within a level no record reads what another writes; slot reuse never clobbers a value
+    that is still to be read."""
+    for seed in range(20):
+        root, _ = circuits.random_circuit(MD, seed, n_nodes=25)
+        for keep in ("all", "ports"):
+            p = compiler.compile_circuit(root, keep=keep)
+            rec, off = p.records.astype(np.int64), p.level_off
+            for lv in range(p.n_levels):
+                r = rec[off[lv]:off[lv + 1]]
+                op = r[:, 0] & 0x7F
+                reads = set()
+                for k in range(len(r)):
+                    ar = compiler.OP_ARITY[int(op[k])]
+                    ins = [r[k, 1], r[k, 2], r[k, 0] >> 8][:ar]
+                    reads.update((int(x), k) for x in ins)
+                writes = {int(r[k, 3]): k for k in range(len(r))}
+                assert len(writes) == len(r)
+                for slot, k in reads:
+                    assert slot not in writes or writes[slot] == k, (seed, keep, lv)
+
+
+def test_pad_levels():
+    rec = np.arange(7 * 4, dtype=np.uint32).reshape(7, 4) + 1
+    off = np.array([0, 3, 3, 7], dtype=np.int32)
+    out, noff = pad_levels(rec, off, 4)
+    assert noff.tolist() == [0, 4, 4, 8]
+    assert np.array_equal(out[:3], rec[:3]) and not out[3].any()
+    assert np.array_equal(out[4:8], rec[3:7])
+
+
+def test_signature_and_stimulus_and_toggles():
+    root = circuits.ripple_adder(MD, 8)
+    eng = B200Engine(root, 1, True, lanes=256, runtime=CpuRuntime())
+    n_bits = eng.randomize_inputs()
+    assert n_bits == 17
+    eng.step()
+    a = sum(eng.get_pin_state(f"/a{i}/pin", lanes=True) << np.uint64(i) for i in range(8))
+    b = sum(eng.get_pin_state(f"/b{i}/pin", lanes=True) << np.uint64(i) for i in range(8))
+    cin = eng.get_pin_state("/cin/pin", lanes=True)
+    s = sum(eng.get_pin_state(f"/s{i}/pin", lanes=True) << np.uint64(i) for i in range(8))
+    s = s + (eng.get_pin_state("/cout/pin", lanes=True) << np.uint64(8))
+    assert np.array_equal(s, a + b + cin)
+    pc, cs = eng.signature()
+    planes = np.stack([eng.get_pin_planes(p)[0] for p in eng.output_pins()])
+    want_pc = np.array([sum(bin(int(w)).count("1") for w in row) for row in planes], dtype=np.uint64)
+    assert np.array_equal(pc, want_pc)
+    from oracle.restate import stimulus_word
+    assert np.array_equal(eng.get_pin_planes("/cin/pin")[0], stimulus_word(0, np.arange(4)))
+    # toggles on the clocked counter: /clk/out flips every step in every lane
+    eng = B200Engine(circuits.counter_circuit(MD), 1, True, lanes=128, runtime=CpuRuntime())
+    eng.enable_toggle_counts(["/clk/out", "/r/out"])
+    eng.run(8)
+    t = eng.toggle_counts()
+    assert t[0] == 8 * 128 and t[1] == 4 * 128 and not t[2:].any()
+
+
+def test_descriptor_api_surface():
+    g = MD.Gate(MD.Gate.XOR, 4, 3, True)
+    assert list(g.all_inputs()) == [("in0", 4), ("in1", 4), ("in2", 4)]
+    assert list(g.all_outputs()) == [("out", 4)] and list(g.all_internals()) == []
+    assert list(MD.Register(3).all_pins()) == [("clock", 1), ("data", 3), ("out", 3), ("prevclock", 1)]
+    assert list(MD.Counter(2).all_pins()) == [("clock", 1), ("out", 2), ("prevclock", 1)]
+    assert list(MD.Clock().all_pins()) == [("out", 1), ("count", 64)]
+    assert list(MD.Adder(5).all_pins()) == [("cin", 1), ("a", 5), ("b", 5), ("cout", 1), ("sum", 5)]
+    assert list(MD.ExposedPin(MD.ExposedPin.IN, 2).all_outputs()) == [("pin", 2)]
+    assert list(MD.ExposedPin(MD.ExposedPin.OUT, 2).all_inputs()) == [("pin", 2)]
+    assert (MD.ExposedPin.IN, MD.ExposedPin.OUT, MD.Gate.AND, MD.Gate.OR, MD.Gate.XOR) == (0, 1, 0, 1, 2)
+    c = MD.Composite()
+    c.add_child("x", MD.ExposedPin(MD.ExposedPin.IN))
+    sub = MD.Composite()
+    sub.add_child("p", MD.ExposedPin(MD.ExposedPin.IN))
+    c.add_child("s", sub)
+    c.add_child("n", MD.Not())
+    c.connect("x", "", "s", "p")
+    c.connect("x", "whatever", "n", "in")
+    assert ("x", "pin", "s/p", "pin") in c.connections and ("x", "pin", "n", "in") in c.connections
+    assert list(c.graph.edges) == [("s", "x"), ("n", "x")]            # dst -> src
+    assert c.graph.nodes["n"]["label"] == "n" and c.get_child("n") is c.graph.nodes["n"]["descriptor"]
+    assert list(c.all_inputs()) == [("x", 1)] and list(c.all_outputs()) == []
+    k = g.clone()
+    assert k is not g and (k.op, k.width, k.num_inputs, k.negated) == (2, 4, 3, True)
+    from mcircuit_b200.core import simulator
+    assert issubclass(simulator.JIT, simulator.Executor)
+    assert list(simulator.iter_simulation_pins(c))[0] == ("/x/pin", 1, "out")

@@ -1,0 +1,182 @@
+"""-m gpu: the CUDA engine (through the C ABI) against the golden vectors harvested from the
+reference JIT and against the oracle on seeded inputs.  Bit-exact: integer work."""
+import numpy as np
+import pytest
+
+import mcircuit_b200.core.descriptors as MD
+from _helpers import (build, compare_engine_to_oracle, golden, lane_trick_planes,
+                      run_register_case, run_trace_case)
+from mcircuit_b200 import circuits, compiler
+from mcircuit_b200.engine import B200Engine
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+TRACES = golden("traces.json")
+
+
+def gpu_factory(mode="resident", keep="all", map_pins=True, **kw):
+    def make(root, burst_size, lanes=64):
+        return B200Engine(root, burst_size, map_pins, lanes=lanes, mode=mode, keep=keep, **kw)
+    return make
+
+
+def test_native_library_is_the_one_running(cuda_rt):
+    assert cuda_rt.cc[0] == 10, "expected a B200 (sm_100)"
+    assert cuda_rt.sm_count >= 100
+    import os
+    maps = open("/proc/self/maps").read()
+    assert "libmcb200.so" in maps
+
+
+@pytest.mark.parametrize("case", TRACES, ids=[c["name"] for c in TRACES])
+@pytest.mark.parametrize("mode,keep,map_pins", [("resident", "all", True), ("levels", "ports", True),
+                                                ("levels", "all", False), ("resident", "ports", False)])
+def test_gpu_traces(case, mode, keep, map_pins):
+    run_trace_case(case, gpu_factory(mode, keep, map_pins), skip_unobservable=(keep == "ports"))
+
+
+def test_gpu_traces_without_tma_and_smem(cuda_rt):
+    """The resident kernel's four variants (TMA record staging on/off, smem state on/off)."""
+    try:
+        for tma in (0, 1):
+            for smem in (0, 1):
+                cuda_rt.set_tuning("resident_tma", tma)
+                cuda_rt.set_tuning("resident_smem", smem)
+                for case in TRACES[:12]:
+                    run_trace_case(case, gpu_factory("resident", "all", True))
+    finally:
+        cuda_rt.set_tuning("resident_tma", 1)
+        cuda_rt.set_tuning("resident_smem", 1)
+
+
+@pytest.mark.parametrize("case", golden("register_intent.json"), ids=lambda c: c["name"])
+@pytest.mark.parametrize("mode", ["resident", "levels"])
+def test_gpu_register_intent(case, mode):
+    run_register_case(case, gpu_factory(mode))
+
+
+@pytest.mark.parametrize("case", golden("adder.json"), ids=lambda c: c["name"])
+def test_gpu_adder(case):
+    w = case["width"]
+    top = MD.Composite()
+    top.add_child("add", MD.Adder(w))
+    vecs = case["vectors"]
+    lanes = (len(vecs) + 63) // 64 * 64
+    pad = lanes - len(vecs)
+    eng = B200Engine(top, 1, True, lanes=lanes)
+    col = lambda k: np.array([v[k] for v in vecs] + [0] * pad, dtype=np.uint64)
+    eng.set_pin_state("/add/a", col(0))
+    eng.set_pin_state("/add/b", col(1))
+    eng.set_pin_state("/add/cin", col(2))
+    eng.step()
+    s = eng.get_pin_state("/add/sum", lanes=True)
+    c = eng.get_pin_state("/add/cout", lanes=True)
+    for i, (ws, wc) in enumerate(case["results"]):
+        assert (int(s[i]), int(c[i])) == (ws, wc), (w, vecs[i])
+
+
+@pytest.mark.parametrize("case", golden("lane_trick.json"), ids=lambda c: c["name"])
+@pytest.mark.parametrize("mode,tile_words", [("levels", None), ("levels", 16), ("resident", None),
+                                             ("resident", 32)])
+def test_gpu_lane_trick(case, mode, tile_words):
+    ins, outs = lane_trick_planes(case)
+    nw = case["n_words"]
+    reps = 1 if tile_words is None else 9
+    eng = B200Engine(build(case), 1, True, lanes=64 * nw * reps, mode=mode, keep="ports",
+                     tile_words=tile_words)
+    for p, words in ins.items():
+        eng.set_pin_planes(p, np.tile(words, reps)[None, :])
+    eng.step()
+    for p, words in outs.items():
+        assert np.array_equal(eng.get_pin_planes(p)[0], np.tile(words, reps)), p
+
+
+@pytest.mark.parametrize("seed", range(200, 240))
+def test_gpu_vs_oracle_all_lanes(seed):
+    root, probes = circuits.random_circuit(MD, seed, n_nodes=22)
+    d = compiler.flatten(root)
+    lane_inputs = [(p, d.pin_width[d.find_pin(p)]) for p in ("/in0/pin", "/in1/pin")]
+    mode = ("resident", "levels")[seed % 2]
+    lanes = (64, 192, 1024, 4160)[seed % 4]
+    compare_engine_to_oracle(lambda M: circuits.random_circuit(M, seed, n_nodes=22),
+                             lambda r, bs, n: gpu_factory(mode)(r, bs, n),
+                             lanes=lanes, steps=6, probes=probes, lane_inputs=lane_inputs, seed=seed)
+
+
+@pytest.mark.parametrize("unroll", [1, 2, 4, 8])
+@pytest.mark.parametrize("cache", [0, 1])
+def test_gpu_level_kernel_variants(cuda_rt, unroll, cache):
+    try:
+        cuda_rt.set_tuning("level_unroll", unroll)
+        cuda_rt.set_tuning("level_cache", cache)
+        case = golden("lane_trick.json")[3]
+        ins, outs = lane_trick_planes(case)
+        nw = case["n_words"]
+        eng = B200Engine(build(case), 1, True, lanes=64 * nw * 7, mode="levels", keep="ports", tile_words=16)
+        for p, words in ins.items():
+            eng.set_pin_planes(p, np.tile(words, 7)[None, :])
+        eng.step()
+        for p, words in outs.items():
+            assert np.array_equal(eng.get_pin_planes(p)[0], np.tile(words, 7)), p
+    finally:
+        cuda_rt.set_tuning("level_unroll", 4)
+        cuda_rt.set_tuning("level_cache", 1)
+
+
+def test_gpu_pack_unpack_stimulus_signature():
+    root = circuits.ripple_adder(MD, 8)
+    eng = B200Engine(root, 1, True, lanes=64 * 37)
+    rng = np.random.default_rng(1)
+    v = rng.integers(0, 2, size=eng.lanes, dtype=np.uint64)
+    eng.set_pin_state("/a3/pin", v)
+    assert np.array_equal(eng.get_pin_state("/a3/pin", lanes=True), v)
+    assert np.array_equal(eng.get_pin_planes("/a3/pin")[0], restate.pack_lanes(v, 1)[0])
+    n_bits = eng.randomize_inputs()
+    assert n_bits == 17
+    ins = eng.input_pins()
+    for s, p in enumerate(ins):
+        assert np.array_equal(eng.get_pin_planes(p)[0], restate.stimulus_word(s, np.arange(eng.words))), p
+    eng.step()
+    pc, cs = eng.signature()
+    planes = np.stack([eng.get_pin_planes(p)[0] for p in eng.output_pins()])
+    want_pc = np.array([sum(bin(int(w)).count("1") for w in row) for row in planes], dtype=np.uint64)
+    cols = np.arange(eng.words, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        want_cs = (planes * (np.uint64(2) * cols + np.uint64(1))[None, :]).sum(axis=1, dtype=np.uint64)
+    assert np.array_equal(pc, want_pc) and np.array_equal(cs, want_cs)
+    # the adder really adds, on every lane
+    a = sum(eng.get_pin_state(f"/a{i}/pin", lanes=True) << np.uint64(i) for i in range(8))
+    b = sum(eng.get_pin_state(f"/b{i}/pin", lanes=True) << np.uint64(i) for i in range(8))
+    s = sum(eng.get_pin_state(f"/s{i}/pin", lanes=True) << np.uint64(i) for i in range(8))
+    s = s + (eng.get_pin_state("/cout/pin", lanes=True) << np.uint64(8))
+    assert np.array_equal(s, a + b + eng.get_pin_state("/cin/pin", lanes=True))
+
+
+def test_gpu_wide_pack_unpack():
+    top = MD.Composite()
+    top.add_child("n", MD.Not(64))
+    eng = B200Engine(top, 1, True, lanes=64 * 5)
+    rng = np.random.default_rng(2)
+    v = rng.integers(0, 2**63, size=eng.lanes, dtype=np.uint64) * np.uint64(2) + np.uint64(1)
+    eng.set_pin_state("/n/in", v)
+    eng.step()
+    assert np.array_equal(eng.get_pin_state("/n/out", lanes=True), ~v)
+    assert eng.get_pin_state("/n/out") == int(~v[0])
+
+
+def test_gpu_toggle_counts():
+    eng = B200Engine(circuits.counter_circuit(MD), 1, True, lanes=128)
+    eng.enable_toggle_counts(["/clk/out", "/r/out"])
+    eng.run(8)
+    t = eng.toggle_counts()
+    assert t[0] == 8 * 128 and t[1] == 4 * 128 and not t[2:].any()
+
+
+def test_gpu_burst_semantics():
+    eng = B200Engine(circuits.counter_circuit(MD), 501, True)
+    for _ in range(8):
+        eng.step()
+    eng.burst()
+    assert (eng.get_pin_state("/clk/out"), eng.get_pin_state("/r/out"), eng.get_pin_state("/r/prevclock")) == (0, 1, 0)
+    with pytest.raises(KeyError):
+        eng.get_pin_state("/r/nope")
