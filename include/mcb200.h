@@ -91,7 +91,7 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
 
 /* K4 - signatures and toggle counts (new capability; no reference counterpart - the
  * reference only peeks one pin at a time, core/simulator.py:285-287).  For each of `n`
- * persistent slots: d_popcount[i] += number of set lane bits, d_checksum[i] += sum over
+ * persistent slots: d_popcount[i] = number of set lane bits, d_checksum[i] = sum over
  * columns j of word * (2 * (col_offset + j) + 1) mod 2^64.  Both are sums, so per-GPU
  * vectors combine with ncclSum.  Columns >= n_words are ignored.                         */
 int mcb_signature(const int32_t *d_slots, int n, const mcb_state *st, int64_t col_offset,
@@ -115,6 +115,13 @@ int mcb_pack(const uint64_t *d_values, int width, const int32_t *d_slots,
              const mcb_state *st, void *stream);
 int mcb_unpack(uint64_t *d_values, int width, const int32_t *d_slots,
                const mcb_state *st, void *stream);
+
+/* Strided host<->device copy of `rows` row segments of `width_bytes` (pinned host memory for
+ * true asynchrony): the bulk form of set/get_pin_state for whole lane tiles, so a tile's
+ * stimulus upload and result download overlap the evaluation of its neighbours.
+ * kind 1 = host to device, 2 = device to host.                                           */
+int mcb_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,
+               int64_t width_bytes, int64_t rows, int kind, void *stream);
 
 /* tuning knobs (block size, gates per block ...); returns the previous value              */
 int mcb_set_tuning(const char *key, int value);

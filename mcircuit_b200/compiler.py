@@ -26,9 +26,10 @@ parallelism:
     level(writer); the reader sees this step's value;
   * self read     (op reads the signal it writes): in place, sees last step's value;
   * back read     (writer later in the sequence): sees last step's value.  If the reader's
-    level is below the writer's it simply reads the live slot before it is overwritten;
-    otherwise the signal gets a shadow ``prev`` slot that the fused end-of-step *latch*
-    level refreshes (``BUF cur -> prev``), and the reader is pointed at the shadow.
+    level is below the writer's it simply reads the live slot before it is overwritten -
+    the writer is pushed one level up when that is all it takes; otherwise the signal gets
+    a shadow ``prev`` slot that the fused end-of-step *latch* level refreshes
+    (``BUF cur -> prev``), and the late readers are pointed at the shadow.
 
 A record is 16 bytes ``{op | in2<<8, in0, in1, out}`` (slot numbers); records are sorted by
 level and ``level_off`` delimits levels.  Slots below ``n_persist`` live for the whole run
@@ -610,13 +611,19 @@ class Program:
 
 
 def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
-                   allow3: Optional[bool] = None) -> Program:
+                   allow3: Optional[bool] = None, back_edges="auto") -> Program:
     """Lower, levelize, allocate slots and encode.  ``keep``: 'all' retains every pin net
     (full drop-in observability); 'ports' retains only what a later step or the caller can
     still need - undriven nets (inputs, constants), state, root-level ports and
     ``observe`` - and recycles the rest."""
     if keep not in ("all", "ports"):
         raise ValueError("keep must be 'all' or 'ports'")
+    # how a read of last step's value is honoured when its reader would otherwise run at or
+    # after the writer: 'order' always delays the writer, 'latch' always uses a shadow slot +
+    # the end-of-step latch level, 'auto' delays the writer when that costs one level.
+    if back_edges not in ("auto", "order", "latch"):
+        raise ValueError("back_edges must be 'auto', 'order' or 'latch'")
+    latch_slack = {"auto": 1, "order": 1 << 30, "latch": 0}[back_edges]
     if allow3 is None:
         allow3 = design.n_signals * 2 + 1024 < IN2_LIMIT
     ops = lower(design, allow3)
@@ -633,10 +640,17 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
             raise CircuitError("net bit %s has more than one driver" % _sig_name(design, o))
         writer[o] = i
 
-    # ---- levels over forward (RAW) edges; collect back reads -----------------------------
+    # ---- levels: RAW edges, and back reads settled by ordering or by a shadow ----------------
+    # An op that reads the OLD value of a signal (its writer comes later in the sequence) only
+    # has to run before that writer.  When the writer is reached we know the levels of all such
+    # readers: if pushing the writer just above them costs at most `latch_slack` levels we do
+    # that (no copy, no extra slot); otherwise the late readers are pointed at a shadow slot
+    # that the end-of-step latch level refreshes.
     level = [0] * n_ops
-    back_reads: List[Tuple[int, int, int]] = []       # (op, operand index, signal)
     has_state_read = bytearray(n_sig)                   # read before written within a step
+    old_readers: Dict[int, List[Tuple[int, int]]] = {}  # signal -> [(op, operand index)]
+    shadow_sig: Dict[int, int] = {}
+    operand = (A, B, C)
     for i in range(n_ops):
         lv = 0
         for k, s in enumerate((A[i], B[i], C[i])):
@@ -652,23 +666,24 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
             else:
                 has_state_read[s] = 1
                 if w > i:
-                    back_reads.append((i, k, s))
+                    old_readers.setdefault(s, []).append((i, k))
+        pending = old_readers.pop(OUT[i], None)
+        if pending:
+            need = 1 + max(level[r] for r, _ in pending)
+            if need > lv:
+                if need - lv <= latch_slack:
+                    lv = need                              # order: writer after its old readers
+                else:
+                    o = OUT[i]
+                    sh = n_sig
+                    n_sig += 1
+                    shadow_sig[o] = sh
+                    writer.append(-2)
+                    for r, k in pending:
+                        if level[r] >= lv:
+                            operand[k][r] = sh             # latch: late readers see the shadow
         level[i] = lv
     n_eval_levels = (max(level) + 1) if n_ops else 0
-
-    # ---- shadows for back reads that cannot simply read the live slot first ---------------
-    shadow_sig: Dict[int, int] = {}
-    operand = (A, B, C)
-    for i, k, s in back_reads:
-        if level[i] < level[writer[s]]:
-            continue                                   # reads cur before it is overwritten
-        sh = shadow_sig.get(s)
-        if sh is None:
-            sh = n_sig
-            n_sig += 1
-            shadow_sig[s] = sh
-            writer.append(-2)
-        operand[k][i] = sh
     has_latch = bool(shadow_sig)
     latch_level = n_eval_levels
     for s, sh in shadow_sig.items():
@@ -763,7 +778,7 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
         raise CircuitError("too many slots")
     if allow3 and n_persist + n_scratch >= IN2_LIMIT:
         # in2 would not fit beside the opcode: redo with 2-input micro-ops only
-        return compile_design(design, keep=keep, observe=observe, allow3=False)
+        return compile_design(design, keep=keep, observe=observe, allow3=False, back_edges=back_edges)
 
     # ---- encode ----------------------------------------------------------------------------
     code_a = np.asarray(code, dtype=np.int64)[order]
@@ -822,5 +837,6 @@ def _sig_name(design: Design, s: int) -> str:
     return "<net %d bit %d>" % (net, bit)
 
 
-def compile_circuit(root, map_pins: bool = True, keep="all", observe: Sequence[str] = ()) -> Program:
-    return compile_design(flatten(root, map_pins), keep=keep, observe=observe)
+def compile_circuit(root, map_pins: bool = True, keep="all", observe: Sequence[str] = (),
+                    back_edges="auto") -> Program:
+    return compile_design(flatten(root, map_pins), keep=keep, observe=observe, back_edges=back_edges)

@@ -51,7 +51,7 @@ static int fail(int code, const char *fmt, ...) {
 // ------------------------------------------------------------------------------------------
 struct Tuning {
     int level_block = 256;      // threads per CTA of the level kernel
-    int level_unroll = 4;       // records in flight per thread (1, 2, 4 or 8)
+    int level_unroll = 2;       // records in flight per thread (1, 2, 4 or 8); 2 measured best
     int level_ctas_per_sm = 0;  // 0: one record batch per CTA; n: persistent, grid ~ sms * n
     int level_cache = 1;        // 0: default loads, 1: L1::no_allocate loads
     int resident_block = 128;   // threads per CTA of the resident kernel
@@ -444,8 +444,8 @@ k_signature(const int *__restrict__ slots, int n, View v, long long col_offset,
         pc = block_sum(pc, sh);
         cs = block_sum(cs, sh);
         if (threadIdx.x == 0) {
-            if (popcount) popcount[i] += pc;
-            if (checksum) checksum[i] += cs;
+            if (popcount) popcount[i] = pc;
+            if (checksum) checksum[i] = cs;
         }
     }
 }
@@ -662,6 +662,18 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
     cudaGraphExecDestroy(exec);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(MCB_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int mcb_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,
+               int64_t width_bytes, int64_t rows, int kind, void *stream) {
+    if (!dst || !src || width_bytes < 0 || rows < 0 || dst_pitch < width_bytes || src_pitch < width_bytes)
+        return fail(MCB_ERR_ARG, "bad copy2d arguments");
+    if (kind != 1 && kind != 2) return fail(MCB_ERR_ARG, "kind must be 1 (H2D) or 2 (D2H)");
+    if (width_bytes == 0 || rows == 0) return 0;
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)dst_pitch, src, (size_t)src_pitch, (size_t)width_bytes,
+                               (size_t)rows, kind == 1 ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost,
+                               (cudaStream_t)stream));
     return 0;
 }
 

@@ -70,7 +70,7 @@ class B200Engine(Executor):
     def __init__(self, root, burst_size=500, map_pins=True, *, lanes=64, device=None,
                  keep="auto", observe: Sequence[str] = (), tile_words: Optional[int] = None,
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
-                 memory_budget: Optional[int] = None):
+                 memory_budget: Optional[int] = None, back_edges="auto"):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -91,7 +91,7 @@ class B200Engine(Executor):
             design = compiler.flatten(root, map_pins)
             if keep == "auto":
                 keep = "all" if (design.n_signals * 3 // 2) * self.stride * 8 <= budget // 2 else "ports"
-            program = compiler.compile_design(design, keep=keep, observe=observe)
+            program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges)
         self.program = program
         self.keep = keep
         P, S = program.n_persist, program.n_scratch
@@ -193,17 +193,59 @@ class B200Engine(Executor):
         self.steps_done += steps
 
     def _run_raw(self, steps):
+        for c0, n in self._tiles():
+            self._run_tile(c0, n, steps)
+
+    def _run_tile(self, c0, n, steps):
+        """All ``steps`` passes of one lane tile (tiles are independent: lanes never interact)."""
         if self.mode == "resident":
             if self._resident is None:
                 rec, off = pad_levels(self.program.records, self.program.level_off)
                 self._resident = (self.rt.to_device(rec), off)
             d_rec, off = self._resident
-            for c0, n in self._tiles():
-                self.rt.run(d_rec, off, self.program.n_levels, self._state_for(c0, n), steps, MODE_RESIDENT)
+            self.rt.run(d_rec, off, self.program.n_levels, self._state_for(c0, n), steps, MODE_RESIDENT)
         else:
-            for c0, n in self._tiles():
-                self.rt.run(self._d_records, self._h_level_off, self.program.n_levels,
-                            self._state_for(c0, n), steps, MODE_LEVELS)
+            self.rt.run(self._d_records, self._h_level_off, self.program.n_levels,
+                        self._state_for(c0, n), steps, MODE_LEVELS)
+
+    def run_host(self, in_plan, h_in, out_plan, h_out, steps: int = 1):
+        """Host buffers in, host buffers out, pipelined by lane tile: the stimulus rows of
+        tile t+1 are uploaded (copy stream) while tile t is evaluated (compute stream) and
+        the result rows of tile t-1 are downloaded (second copy stream).  ``h_in`` /
+        ``h_out``: pinned int64 tensors [n_bits, words] in the row order of the io plans
+        (bit planes, the layout of ``get_pin_planes``).  Returns after enqueueing; the
+        caller's current stream is joined with the download stream."""
+        torch = self.rt.torch
+        dev = self.rt.device
+        if getattr(self, "_copy_streams", None) is None:
+            self._copy_streams = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        s_in, s_out = self._copy_streams
+        main = torch.cuda.current_stream(dev)
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        base = self._plane.data_ptr()
+        pitch = self.stride * 8
+        in_pitch, out_pitch = h_in.stride(0) * 8, h_out.stride(0) * 8
+        tiles = list(self._tiles())
+        ready = []
+        for c0, n in tiles:
+            for first, count, k in in_plan["runs"]:
+                self.rt.copy2d(base + (first * self.stride + c0) * 8, pitch,
+                               h_in.data_ptr() + k * in_pitch + c0 * 8, in_pitch, n * 8, count, True, s_in)
+            ev = torch.cuda.Event()
+            ev.record(s_in)
+            ready.append(ev)
+        for (c0, n), ev in zip(tiles, ready):
+            main.wait_event(ev)
+            self._run_tile(c0, n, steps)
+            done = torch.cuda.Event()
+            done.record(main)
+            s_out.wait_event(done)
+            for first, count, k in out_plan["runs"]:
+                self.rt.copy2d(h_out.data_ptr() + k * out_pitch + c0 * 8, out_pitch,
+                               base + (first * self.stride + c0) * 8, pitch, n * 8, count, False, s_out)
+        main.wait_stream(s_out)
+        self.steps_done += int(steps)
 
     # ---- pins --------------------------------------------------------------------------------------
     def _slots_of(self, pin: str, need_value=True):
@@ -364,7 +406,6 @@ class B200Engine(Executor):
 
     def signature_run(self, plan):
         buf, n, half = plan["buf"], plan["n"], plan["half"]
-        buf[:] = 0
         if n:
             self.rt.signature(plan["d_slots"], n, self._whole, self.lane_word_offset,
                               buf[:half], buf[half:])

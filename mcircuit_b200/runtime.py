@@ -54,6 +54,7 @@ _PROTOTYPES = [
     ("mcb_fill_rows", c_int, [c_void_p, c_void_p, c_int, POINTER(McbState), c_void_p]),
     ("mcb_pack", c_int, [c_void_p, c_int, c_void_p, POINTER(McbState), c_void_p]),
     ("mcb_unpack", c_int, [c_void_p, c_int, c_void_p, POINTER(McbState), c_void_p]),
+    ("mcb_copy2d", c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     ("mcb_set_tuning", c_int, [c_char_p, c_int]),
     ("mcb_launch_count", c_int64, [c_int]),
 ]
@@ -207,6 +208,13 @@ class CudaRuntime:
         with self.torch.cuda.device(self.device):
             self._check(self.lib.mcb_unpack(
                 d_values.data_ptr(), int(width), d_slots.data_ptr(), ctypes.byref(st), self._stream()))
+
+    def copy2d(self, dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, h2d: bool, stream=None):
+        st = c_void_p(stream.cuda_stream) if stream is not None else self._stream()
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.mcb_copy2d(c_void_p(dst_ptr), int(dst_pitch), c_void_p(src_ptr),
+                                            int(src_pitch), int(width_bytes), int(rows),
+                                            1 if h2d else 2, st))
 
     def set_tuning(self, key: str, value: int) -> int:
         return self.lib.mcb_set_tuning(key.encode(), int(value))

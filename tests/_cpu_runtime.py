@@ -163,9 +163,9 @@ class CpuRuntime:
         with np.errstate(over="ignore"):
             if d_popcount is not None:
                 pc = np.array([sum(bin(int(w)).count("1") for w in r) for r in rows], dtype=U64)
-                d_popcount[:n] += pc
+                d_popcount[:n] = pc
             if d_checksum is not None:
-                d_checksum[:n] += (rows * (U64(2) * cols + U64(1))[None, :]).sum(axis=1, dtype=U64)
+                d_checksum[:n] = (rows * (U64(2) * cols + U64(1))[None, :]).sum(axis=1, dtype=U64)
         self._launches += 1
 
     def toggle_accum(self, d_slots, n, st, d_shadow, shadow_stride, d_toggles):

@@ -27,6 +27,24 @@ def test_engine_traces(case, mode, keep, map_pins):
     run_trace_case(case, engine_factory(mode, keep, map_pins), skip_unobservable=(keep == "ports"))
 
 
+@pytest.mark.parametrize("case", TRACES, ids=[c["name"] for c in TRACES])
+@pytest.mark.parametrize("back_edges", ["order", "latch"])
+def test_engine_traces_back_edge_policies(case, back_edges):
+    """Reads of last step's value: settled by ordering or by shadow slot + latch level."""
+    run_trace_case(case, engine_factory("levels", "all", True, back_edges=back_edges))
+
+
+def test_back_edge_policies_shape():
+    root, _ = circuits.random_circuit(MD, 0, n_nodes=20)
+    order = compiler.compile_circuit(root, back_edges="order")
+    latch = compiler.compile_circuit(root, back_edges="latch")
+    assert not order.has_latch and not order.sig_shadow
+    assert latch.has_latch and latch.sig_shadow and latch.n_ops == order.n_ops + len(latch.sig_shadow)
+    assert latch.n_gates == order.n_gates
+    c4 = compiler.compile_circuit(circuits.lfsr_pipeline(MD, 4, 8, 6, taps=(7, 5, 1, 0)))
+    assert not c4.sig_shadow          # prevclock read-then-write is settled by ordering
+
+
 @pytest.mark.parametrize("case", golden("register_intent.json"), ids=lambda c: c["name"])
 def test_engine_register_intent(case):
     run_register_case(case, engine_factory("levels"))

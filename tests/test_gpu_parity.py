@@ -35,6 +35,13 @@ def test_gpu_traces(case, mode, keep, map_pins):
     run_trace_case(case, gpu_factory(mode, keep, map_pins), skip_unobservable=(keep == "ports"))
 
 
+@pytest.mark.parametrize("back_edges", ["order", "latch"])
+def test_gpu_traces_back_edge_policies(back_edges):
+    for case in TRACES:
+        for mode in ("levels", "resident"):
+            run_trace_case(case, gpu_factory(mode, "all", True, back_edges=back_edges))
+
+
 def test_gpu_traces_without_tma_and_smem(cuda_rt):
     """The resident kernel's four variants (TMA record staging on/off, smem state on/off)."""
     try:
@@ -180,3 +187,27 @@ def test_gpu_burst_semantics():
     assert (eng.get_pin_state("/clk/out"), eng.get_pin_state("/r/out"), eng.get_pin_state("/r/prevclock")) == (0, 1, 0)
     with pytest.raises(KeyError):
         eng.get_pin_state("/r/nope")
+
+
+def test_gpu_run_host_pipelined_matches_resident():
+    """Host buffers in / out through the tile-pipelined path == device-resident run."""
+    import torch
+    root = circuits.random_dag(MD, n_gates=3000, depth=15, n_inputs=48, seed=9)
+    lanes = 64 * 200
+    a = B200Engine(root, 1, True, lanes=lanes, mode="levels", keep="ports", tile_words=32)
+    b = B200Engine(root, 1, True, lanes=lanes, mode="levels", keep="ports", tile_words=32)
+    assert a.n_tiles == 7
+    a.randomize_inputs()
+    a.step()
+    in_plan, out_plan = b.io_plan(b.input_pins()), b.io_plan(b.output_pins())
+    h_in = torch.empty((in_plan["n"], b.words), dtype=torch.int64, pin_memory=True)
+    h_out = torch.zeros((out_plan["n"], b.words), dtype=torch.int64, pin_memory=True)
+    stim = restate.stimulus_word(np.arange(48)[:, None], np.arange(b.words)[None, :])
+    h_in.numpy()[:] = stim.view(np.int64)
+    b.run_host(in_plan, h_in, out_plan, h_out)
+    torch.cuda.synchronize()
+    for k, p in enumerate(b.output_pins()):
+        assert np.array_equal(h_out[k].numpy().view(np.uint64), a.get_pin_planes(p)[0]), p
+    pa, ca = a.signature()
+    pb, cb = b.signature()
+    assert np.array_equal(pa, pb) and np.array_equal(ca, cb)
