@@ -50,7 +50,7 @@ static int fail(int code, const char *fmt, ...) {
 // tuning knobs
 // ------------------------------------------------------------------------------------------
 struct Tuning {
-    int level_block = 256;      // threads per CTA of the level kernel
+    int level_block = 128;      // threads per CTA of the level kernel (128 measured best)
     int level_unroll = 2;       // records in flight per thread (1, 2, 4 or 8); 2 measured best
     int level_ctas_per_sm = 0;  // 0: one record batch per CTA; n: persistent, grid ~ sms * n
     int level_cache = 1;        // 0: default loads, 1: L1::no_allocate loads
