@@ -325,10 +325,11 @@ def run_ours(a):
                       "-> signature -> D2H (pinned host buffers)"}
         assert np.array_equal(h_sig.numpy().view(np.uint64), signature_host), "e2e signature differs from resident run"
         # the downloaded planes really are the outputs: their popcounts are the signature
+        local_sig = eng.rt.to_host_u64(eng.signature_run(sig))       # this rank's shard, not reduced
         idx = list(range(0, n_out, max(1, n_out // 16)))
         for i in idx:
             pc = int(np.unpackbits(h_out[i].numpy().view(np.uint8)).sum())
-            assert pc == int(signature_host[i]), "downloaded output plane %d does not match its signature" % i
+            assert pc == int(local_sig[i]), "downloaded output plane %d does not match its signature" % i
         e2e["downloaded_planes_checked_against_signature"] = len(idx)
 
     # ---- optional parity spot-check against the oracle on sampled columns -----------------------------
