@@ -89,6 +89,16 @@ int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void 
 int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
             const mcb_state *st, int64_t steps, int mode, void *stream);
 
+/* K1p - all levels of one lane tile in ONE cooperative launch with a grid barrier between
+ * levels (same replaced interface as mcb_eval_levels / mcb_run).  Meant for small tiles
+ * (<= 512 lane words) whose per-level rows stay in L2 from one level to the next.  The record
+ * stream may carry operand hints: bit 31 of in0 / in1 = "producer is two or more levels back:
+ * stream it through L2"; slot numbers are the low 31 bits.  `d_level_off` is the device copy
+ * of `h_level_off`.                                                                        */
+int mcb_run_persistent(const uint32_t *d_records, const int32_t *d_level_off,
+                       const int32_t *h_level_off, int n_levels, const mcb_state *st,
+                       int64_t steps, void *stream);
+
 /* K4 - signatures and toggle counts (new capability; no reference counterpart - the
  * reference only peeks one pin at a time, core/simulator.py:285-287).  For each of `n`
  * persistent slots: d_popcount[i] = number of set lane bits, d_checksum[i] = sum over

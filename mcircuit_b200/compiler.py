@@ -587,6 +587,7 @@ class Program:
     gate_words_bytes: int          # algorithmic bytes per lane-word per step
     constants: List[Tuple[int, int, int]]   # (first signal, width, value) poked after build
     max_level_gates: int = 0
+    records_hinted: Optional[np.ndarray] = None   # records + streaming hints (bit 31 of in0/in1)
 
     @property
     def n_slots(self) -> int:
@@ -802,6 +803,30 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
     records[:, 2] = sb.astype(np.uint32)
     records[:, 3] = so.astype(np.uint32)
 
+    # operand hints for the persistent level kernel (bit 31 of in0 / in1): "stream" when the
+    # value was produced two or more levels back (or never, i.e. an input): it is not in L2
+    # any more and should not push the previous level's rows out on its way through.
+    wr = np.asarray(writer, dtype=np.int64)
+    lvl_ord = level_arr[order]
+    seq_ord = order
+
+    def stream_hint(x):
+        h = np.zeros(len(x), dtype=bool)
+        m = x >= 0
+        w = np.full(len(x), -1, dtype=np.int64)
+        w[m] = wr[x[m]]
+        never = m & (w < 0)
+        fwd = m & (w >= 0) & (w < seq_ord)
+        h[never] = True
+        wl = np.zeros(len(x), dtype=np.int64)
+        wl[fwd] = level_arr[w[fwd]]
+        h[fwd] = (lvl_ord[fwd] - wl[fwd]) >= 2
+        return h
+
+    records_hinted = records.copy()
+    records_hinted[:, 1] |= (stream_hint(a_a).astype(np.uint32) << np.uint32(31))
+    records_hinted[:, 2] |= (stream_hint(b_a).astype(np.uint32) << np.uint32(31))
+
     is_gate = np.asarray(ops.is_gate, dtype=bool)
     n_gates = int(is_gate.sum())
     arity = np.zeros(256, dtype=np.int64)
@@ -823,7 +848,8 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
         n_levels=n_levels, has_latch=has_latch, n_persist=n_persist, n_scratch=n_scratch,
         sig_slot=sig_slot, sig_shadow={s: int(sig_slot[sh]) for s, sh in shadow_sig.items()},
         sig_kept=kept, n_gates=n_gates, n_ops=n_total, gate_words_bytes=gw_bytes,
-        constants=constants, max_level_gates=int(counts.max()) if n_total else 0)
+        constants=constants, max_level_gates=int(counts.max()) if n_total else 0,
+        records_hinted=records_hinted)
 
 
 def _sig_name(design: Design, s: int) -> str:

@@ -6,8 +6,19 @@ module-level helpers the reference exports - and that its GUI imports (``app.py:
 re-provided with identical outputs but linear cost (the reference's are
 O(nodes x connections)).
 """
-from ..compiler import _SCHED_EMIT, flatten
-from ..engine import B200Engine, Executor
+try:
+    from ..compiler import _SCHED_EMIT, flatten
+    from ..engine import B200Engine, Executor
+except ImportError:
+    # drop-in mode: ``mcircuit_b200/`` itself is on sys.path, so this module is the top-level
+    # ``core.simulator`` exactly like the reference's; reach the rest of the package by name.
+    # (The compiler is duck-typed on descriptor class names, so descriptors imported as
+    # ``core.descriptors`` and as ``mcircuit_b200.core.descriptors`` both work.)
+    import os as _os
+    import sys as _sys
+    _sys.path.insert(0, _os.path.dirname(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))))
+    from mcircuit_b200.compiler import _SCHED_EMIT, flatten
+    from mcircuit_b200.engine import B200Engine, Executor
 
 __all__ = ["Executor", "B200Engine", "JIT", "iter_simulation_pins",
            "iter_simulation_connections", "iter_simulation_topology", "_map_to_sources"]

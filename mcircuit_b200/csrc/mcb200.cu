@@ -13,6 +13,8 @@
 #include <string.h>
 #include <stdarg.h>
 #include <atomic>
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 #include "../../include/mcb200.h"
 
@@ -58,6 +60,10 @@ struct Tuning {
     int resident_tma = 1;       // stage the record stream with cp.async.bulk + mbarrier
     int resident_smem = 1;      // keep state in shared memory when it fits
     int graph_min_steps = 2;    // mode 1: capture a graph when steps >= this
+    int persist_unroll = 2;     // records per thread batch of the persistent level kernel
+    int persist_hints = 1;      // honour the operand streaming hints (bit 31)
+    int persist_ctas_per_sm = 1;  // 0: as many as fit
+    int persist_block = 1024;   // threads per CTA of the persistent level kernel
 };
 static Tuning g_tune;
 static int g_sm_count = 0;
@@ -215,6 +221,127 @@ static int launch_level(const uint4 *recs, int n, const View &v, cudaStream_t s)
     else MCB_LL(1);
 #undef MCB_LL
     LAUNCH_CHECK("k_eval_level");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1p: all levels of one lane tile in ONE cooperative launch, a grid barrier between levels.
+// With a small tile (<= 512 words) one level's output rows (5,000 x 4 KB = 20 MB for C5) are
+// still in the 126 MB L2 when the next level reads them as fan-in, and recycled scratch
+// slots are rewritten before their dirty lines are ever evicted, so DRAM traffic drops below
+// the algorithmic 24 B per gate-word.  Per-level kernel launches cannot exploit this (a 10 us
+// level pays 3 us of launch gap); a grid barrier costs about 1 us.  Operand bit 31 (set by
+// the compiler when the producer is two or more levels back) selects an L2 evict-first
+// policy for the streaming fan-in so it does not push the recent rows out.  Loads never
+// allocate in L1 (it is not coherent across SMs within a launch).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t make_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t make_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ ulonglong2 ld_state2_hint(const uint64_t *p, uint64_t policy) {
+    ulonglong2 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+                 : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ void st_state2_hint(uint64_t *p, ulonglong2 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;"
+                 :: "l"(p), "l"(v.x), "l"(v.y), "l"(policy) : "memory");
+}
+
+#define SLOT_MASK 0x7fffffffu
+
+template <int U, int HINTS>
+__global__ void __launch_bounds__(1024, 1)
+k_eval_persistent(const uint4 *__restrict__ recs, const int *__restrict__ level_off, int n_levels,
+                  View v, long long n_vec, long long steps) {
+    cg::grid_group grid = cg::this_grid();
+    const uint64_t pol_stream = make_policy_evict_first();
+    const uint64_t pol_keep = make_policy_evict_last();
+    const unsigned nv = (unsigned)n_vec;
+    for (long long step = 0; step < steps; ++step) {
+        for (int lv = 0; lv < n_levels; ++lv) {
+            const int lo = level_off[lv];
+            const int n = level_off[lv + 1] - lo;
+            const int batches = (n + U - 1) / U;
+            // work index = batch * n_vec + column pair (column fastest: a warp stays inside one
+            // batch whenever n_vec is a multiple of 32, so its record loads are broadcasts)
+            const unsigned long long work = (unsigned long long)batches * nv;
+            for (unsigned long long w0 = (unsigned long long)blockIdx.x * blockDim.x; w0 < work;
+                 w0 += (unsigned long long)gridDim.x * blockDim.x) {
+                const unsigned long long w = w0 + threadIdx.x;
+                if (w >= work) continue;
+                const unsigned b = (unsigned)(w / nv);
+                const long long off = (long long)(w - (unsigned long long)b * nv) * 2;
+                const int g0 = lo + (int)b * U;
+                uint4 r[U];
+                ulonglong2 x[U], y[U], z[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    r[u] = (g0 + u < lo + n) ? __ldg(recs + g0 + u) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t op = r[u].x & 0x7f;
+                    x[u] = y[u] = z[u] = make_ulonglong2(0, 0);
+                    if (op != MCB_OP_NOP) {
+                        if (HINTS) {
+                            x[u] = ld_state2_hint(row(v, r[u].y & SLOT_MASK) + off,
+                                                  (r[u].y >> 31) ? pol_stream : pol_keep);
+                            if (op != MCB_OP_BUF)
+                                y[u] = ld_state2_hint(row(v, r[u].z & SLOT_MASK) + off,
+                                                      (r[u].z >> 31) ? pol_stream : pol_keep);
+                        } else {
+                            x[u] = ld_state2<1>(row(v, r[u].y & SLOT_MASK) + off);
+                            if (op != MCB_OP_BUF) y[u] = ld_state2<1>(row(v, r[u].z & SLOT_MASK) + off);
+                        }
+                        if (op >= MCB_OP_MUX) z[u] = ld_state2<1>(row(v, r[u].x >> 8) + off);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t op = r[u].x & 0xff;
+                    if ((op & 0x7f) != MCB_OP_NOP) {
+                        ulonglong2 o;
+                        o.x = apply_op(op, x[u].x, y[u].x, z[u].x);
+                        o.y = apply_op(op, x[u].y, y[u].y, z[u].y);
+                        if (HINTS) st_state2_hint(row(v, r[u].w & SLOT_MASK) + off, o, pol_keep);
+                        else st_state2(row(v, r[u].w & SLOT_MASK) + off, o);
+                    }
+                }
+            }
+            grid.sync();
+        }
+    }
+}
+
+template <int U, int HINTS>
+static int launch_persistent_t(const uint4 *recs, const int *d_level_off, int n_levels, View v,
+                               long long steps, int max_level, cudaStream_t s) {
+    long long n_vec = (v.n_words + 1) / 2;
+    int block = g_tune.persist_block;
+    if (block > 1024) block = 1024;
+    if (block < 32) block = 32;
+    block = block / 32 * 32;
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_eval_persistent<U, HINTS>, block, 0));
+    if (per_sm < 1) return fail(MCB_ERR_CUDA, "persistent kernel does not fit on an SM");
+    if (g_tune.persist_ctas_per_sm > 0 && per_sm > g_tune.persist_ctas_per_sm) per_sm = g_tune.persist_ctas_per_sm;
+    const long long work = (long long)((max_level + U - 1) / U) * n_vec;
+    long long grid = (long long)sm_count() * per_sm;     // few, fat CTAs: the grid barrier is
+    if (grid > (work + block - 1) / block) grid = (work + block - 1) / block;   // one atomic per CTA
+    if (grid < 1) grid = 1;
+    void *args[] = {(void *)&recs, (void *)&d_level_off, (void *)&n_levels, (void *)&v, (void *)&n_vec,
+                    (void *)&steps};
+    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_eval_persistent<U, HINTS>, dim3((unsigned)grid),
+                                         dim3(block), args, 0, s));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
 
@@ -564,6 +691,10 @@ int mcb_set_tuning(const char *key, int value) {
     else if (!strcmp(key, "resident_tma")) p = &g_tune.resident_tma;
     else if (!strcmp(key, "resident_smem")) p = &g_tune.resident_smem;
     else if (!strcmp(key, "graph_min_steps")) p = &g_tune.graph_min_steps;
+    else if (!strcmp(key, "persist_unroll")) p = &g_tune.persist_unroll;
+    else if (!strcmp(key, "persist_hints")) p = &g_tune.persist_hints;
+    else if (!strcmp(key, "persist_ctas_per_sm")) p = &g_tune.persist_ctas_per_sm;
+    else if (!strcmp(key, "persist_block")) p = &g_tune.persist_block;
     else return fail(MCB_ERR_ARG, "unknown tuning key %s", key);
     int old = *p;
     *p = value;
@@ -663,6 +794,32 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return fail(MCB_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+int mcb_run_persistent(const uint32_t *d_records, const int32_t *d_level_off,
+                       const int32_t *h_level_off, int n_levels, const mcb_state *st, int64_t steps,
+                       void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (!d_records || !d_level_off || !h_level_off || n_levels < 0 || steps < 0)
+        return fail(MCB_ERR_ARG, "bad persistent-run arguments");
+    if (steps == 0 || n_levels == 0 || st->n_words == 0) return 0;
+    int max_level = 0;
+    for (int l = 0; l < n_levels; ++l) {
+        const int n = h_level_off[l + 1] - h_level_off[l];
+        if (n > max_level) max_level = n;
+    }
+    const View v = make_view(st);
+    const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
+    const int H = g_tune.persist_hints ? 1 : 0;
+    cudaStream_t s = (cudaStream_t)stream;
+#define MCB_LP(UU)                                                                         \
+    (H ? launch_persistent_t<UU, 1>(recs, d_level_off, n_levels, v, steps, max_level, s)    \
+       : launch_persistent_t<UU, 0>(recs, d_level_off, n_levels, v, steps, max_level, s))
+    if (g_tune.persist_unroll >= 4) return MCB_LP(4);
+    if (g_tune.persist_unroll >= 2) return MCB_LP(2);
+    return MCB_LP(1);
+#undef MCB_LP
 }
 
 int mcb_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,

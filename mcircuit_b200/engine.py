@@ -102,8 +102,8 @@ class B200Engine(Executor):
         if mode == "auto":
             # per-level launches pay off only when one level keeps the whole GPU busy
             mode = "levels" if avg_level * min(self.words, DEFAULT_TILE_WORDS) >= (1 << 19) else "resident"
-        if mode not in ("levels", "resident"):
-            raise ValueError("mode must be 'auto', 'levels' or 'resident'")
+        if mode not in ("levels", "resident", "persistent"):
+            raise ValueError("mode must be 'auto', 'levels', 'resident' or 'persistent'")
         self.mode = mode
 
         # ---- tiling ------------------------------------------------------------------------------
@@ -199,7 +199,14 @@ class B200Engine(Executor):
 
     def _run_tile(self, c0, n, steps):
         """All ``steps`` passes of one lane tile (tiles are independent: lanes never interact)."""
-        if self.mode == "resident":
+        if self.mode == "persistent":
+            if getattr(self, "_persistent", None) is None:
+                self._persistent = (self.rt.to_device(self.program.records_hinted),
+                                    self.rt.to_device(self._h_level_off))
+            d_rec, d_off = self._persistent
+            self.rt.run_persistent(d_rec, d_off, self._h_level_off, self.program.n_levels,
+                                   self._state_for(c0, n), steps)
+        elif self.mode == "resident":
             if self._resident is None:
                 rec, off = pad_levels(self.program.records, self.program.level_off)
                 self._resident = (self.rt.to_device(rec), off)

@@ -19,6 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libmcb200.so")
 
 MODE_RESIDENT = 0
 MODE_LEVELS = 1
+MODE_PERSISTENT = 2
 RESIDENT_UNROLL = 4
 
 
@@ -45,6 +46,8 @@ _PROTOTYPES = [
     ("mcb_eval_levels", c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(McbState), c_void_p]),
     ("mcb_latch", c_int, [c_void_p, c_int, POINTER(McbState), c_void_p]),
     ("mcb_run", c_int, [c_void_p, c_void_p, c_int, POINTER(McbState), c_int64, c_int, c_void_p]),
+    ("mcb_run_persistent", c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(McbState), c_int64,
+                                   c_void_p]),
     ("mcb_signature", c_int, [c_void_p, c_int, POINTER(McbState), c_int64, c_void_p, c_void_p,
                               c_void_p]),
     ("mcb_toggle_accum", c_int, [c_void_p, c_int, POINTER(McbState), c_void_p, c_int64, c_void_p,
@@ -174,6 +177,12 @@ class CudaRuntime:
             self._check(self.lib.mcb_run(
                 d_records.data_ptr(), h_level_off.ctypes.data, int(n_levels), ctypes.byref(st),
                 int(steps), int(mode), self._stream()))
+
+    def run_persistent(self, d_records, d_level_off, h_level_off: np.ndarray, n_levels, st: McbState, steps):
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.mcb_run_persistent(
+                d_records.data_ptr(), d_level_off.data_ptr(), h_level_off.ctypes.data, int(n_levels),
+                ctypes.byref(st), int(steps), self._stream()))
 
     def signature(self, d_slots, n, st: McbState, col_offset, d_popcount, d_checksum):
         with self.torch.cuda.device(self.device):

@@ -156,6 +156,14 @@ class CpuRuntime:
             for _ in range(int(steps)):
                 self.eval_levels(d_records, h_level_off, 0, n_levels, st)
 
+    def run_persistent(self, d_records, d_level_off, h_level_off, n_levels, st, steps):
+        recs = d_records.astype(np.int64)
+        recs[:, 1] &= 0x7FFFFFFF          # strip the streaming hints
+        recs[:, 2] &= 0x7FFFFFFF
+        assert np.array_equal(np.asarray(d_level_off), np.asarray(h_level_off))
+        for _ in range(int(steps)):
+            self.eval_levels(recs, h_level_off, 0, n_levels, st)
+
     # ---- K4 / K5 ---------------------------------------------------------------------------------
     def signature(self, d_slots, n, st, col_offset, d_popcount, d_checksum):
         rows = st.read(d_slots[:n])

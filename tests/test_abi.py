@@ -61,3 +61,14 @@ def test_product_has_no_cpu_fallback():
     from mcircuit_b200.runtime import EngineUnavailable
     with pytest.raises(EngineUnavailable):
         B200Engine(circuits.counter_circuit(), 1, True)
+
+
+def test_product_never_imports_oracle():
+    """oracle/ is test infrastructure: nothing under mcircuit_b200/ may import or load it."""
+    pkg = os.path.join(ROOT, "mcircuit_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "libmcref" not in text and "_cpu_runtime" not in text, f

@@ -22,7 +22,7 @@ def engine_factory(mode="resident", keep="all", map_pins=True, **kw):
 
 @pytest.mark.parametrize("case", TRACES, ids=[c["name"] for c in TRACES])
 @pytest.mark.parametrize("mode,keep,map_pins", [("resident", "all", True), ("levels", "ports", True),
-                                                ("levels", "all", False)])
+                                                ("levels", "all", False), ("persistent", "ports", True)])
 def test_engine_traces(case, mode, keep, map_pins):
     run_trace_case(case, engine_factory(mode, keep, map_pins), skip_unobservable=(keep == "ports"))
 
@@ -274,3 +274,16 @@ def test_descriptor_api_surface():
     from mcircuit_b200.core import simulator
     assert issubclass(simulator.JIT, simulator.Executor)
     assert list(simulator.iter_simulation_pins(c))[0] == ("/x/pin", 1, "out")
+
+
+def test_streaming_hints_shape():
+    root = circuits.random_dag(MD, n_gates=600, depth=12, n_inputs=16, seed=5)
+    p = compiler.compile_circuit(root, keep="ports")
+    h = p.records_hinted
+    assert np.array_equal(h[:, [0, 3]], p.records[:, [0, 3]])
+    assert np.array_equal(h[:, 1:3] & 0x7FFFFFFF, p.records[:, 1:3])
+    lv0 = slice(p.level_off[0], p.level_off[1])
+    assert (h[lv0, 1] >> 31).all() and (h[lv0, 2] >> 31).all()          # level 0 reads inputs only
+    lv5 = slice(p.level_off[5], p.level_off[6])
+    assert not (h[lv5, 1] >> 31).any()                                   # in0 comes from level 4
+    assert (h[lv5, 2] >> 31).mean() > 0.5                                # in1 mostly from far back

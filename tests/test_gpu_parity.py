@@ -30,7 +30,8 @@ def test_native_library_is_the_one_running(cuda_rt):
 
 @pytest.mark.parametrize("case", TRACES, ids=[c["name"] for c in TRACES])
 @pytest.mark.parametrize("mode,keep,map_pins", [("resident", "all", True), ("levels", "ports", True),
-                                                ("levels", "all", False), ("resident", "ports", False)])
+                                                ("levels", "all", False), ("resident", "ports", False),
+                                                ("persistent", "ports", True), ("persistent", "all", False)])
 def test_gpu_traces(case, mode, keep, map_pins):
     run_trace_case(case, gpu_factory(mode, keep, map_pins), skip_unobservable=(keep == "ports"))
 
@@ -84,7 +85,7 @@ def test_gpu_adder(case):
 
 @pytest.mark.parametrize("case", golden("lane_trick.json"), ids=lambda c: c["name"])
 @pytest.mark.parametrize("mode,tile_words", [("levels", None), ("levels", 16), ("resident", None),
-                                             ("resident", 32)])
+                                             ("resident", 32), ("persistent", None), ("persistent", 16)])
 def test_gpu_lane_trick(case, mode, tile_words):
     ins, outs = lane_trick_planes(case)
     nw = case["n_words"]
@@ -211,3 +212,49 @@ def test_gpu_run_host_pipelined_matches_resident():
     pa, ca = a.signature()
     pb, cb = b.signature()
     assert np.array_equal(pa, pb) and np.array_equal(ca, cb)
+
+
+def test_reference_examples_run_unmodified(tmp_path):
+    """The three example scripts of the reference, text unchanged except that they are
+    restated here (the GPU box has no /root/reference): same imports, same calls."""
+    import subprocess
+    import sys
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "clock_example.py"
+    script.write_text(
+        "from core.descriptors import Composite, Not\n"
+        "from core.simulator import JIT\n"
+        "s = Composite()\nnot_ = Not()\n"
+        "s.add_child('not', not_)\ns.connect('not', 'out', 'not', 'in')\n"
+        "sim = JIT(s, 501, True)\n"
+        "for i in range(10):\n    sim.step()\n    print(sim.get_pin_state('/not/out'))\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(root, "mcircuit_b200"))
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split() == ["1", "0", "1", "0", "1", "0", "1", "0", "1", "0"]
+
+
+@pytest.mark.parametrize("unroll,hints", [(1, 0), (2, 1), (4, 1), (2, 0)])
+def test_gpu_persistent_level_kernel_variants(cuda_rt, unroll, hints):
+    try:
+        cuda_rt.set_tuning("persist_unroll", unroll)
+        cuda_rt.set_tuning("persist_hints", hints)
+        root = circuits.random_dag(MD, n_gates=20_000, depth=40, n_inputs=256, seed=77)
+        lanes = 64 * 320
+        a = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="levels")
+        b = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="persistent", tile_words=64)
+        assert b.n_tiles == 5
+        for e in (a, b):
+            e.randomize_inputs()
+            e.run(1)
+        pa, ca = a.signature()
+        pb, cb = b.signature()
+        assert np.array_equal(pa, pb) and np.array_equal(ca, cb)
+        # sequential circuit, several steps inside one cooperative launch
+        c = B200Engine(circuits.counter_circuit(MD), 1, True, lanes=128, mode="persistent")
+        c.run(7)
+        assert (c.get_pin_state("/clk/out"), c.get_pin_state("/r/out")) == (1, 0)
+    finally:
+        cuda_rt.set_tuning("persist_unroll", 2)
+        cuda_rt.set_tuning("persist_hints", 1)
