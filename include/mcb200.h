@@ -81,10 +81,14 @@ int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void 
 
 /* K3 - resident multi-step run.  Replaces `burst()` (core/simulator.py:225-245, :296-297)
  * without its off-by-one: runs exactly `steps` steps; the Python `burst()` passes
- * burst_size + 1.  mode 0: one persistent kernel, each thread owns lane columns and walks
- * the whole record stream (every level padded by the host to a multiple of
- * MCB_RESIDENT_UNROLL records with NOPs, so a batch never straddles a level); mode 1: per-level launches captured once in a
- * CUDA graph and replayed `steps` times.                                                  */
+ * burst_size + 1.  mode 0: one persistent kernel, each thread owns (a slice of) a lane column
+ * and walks the whole record stream, which the host has arranged in batches of B
+ * independent records of ONE base opcode (padded with records on a private trash slot; every
+ * load of a batch may be issued before its first store); `h_level_off` then only has to
+ * delimit segments that are multiples of B.
+ * Bits 8..15 of `mode` carry B (0 = MCB_RESIDENT_UNROLL; 4 or 8), bits 16..23 the bytes
+ * of a lane word one thread owns (0 = automatic; 8, 4, 2 or 1).  mode 1: per-level launches
+ * captured once in a CUDA graph and replayed `steps` times.                               */
 #define MCB_RESIDENT_UNROLL 4
 int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
             const mcb_state *st, int64_t steps, int mode, void *stream);

@@ -852,6 +852,45 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
         records_hinted=records_hinted)
 
 
+def schedule_batches(records: np.ndarray, level_off: np.ndarray, trash_slot: int, batch: int = 8):
+    """Arrange a level-sorted record stream into batches of ``batch`` records for the resident
+    kernel: every batch holds records of ONE base opcode from ONE level (records of a level
+    are mutually independent, so the kernel may issue all loads of a batch before its first
+    store), padded with records that read and write ``trash_slot`` - a private row nobody
+    else uses - so the kernel needs no per-record opcode or NOP test.  The complement flag
+    (bit 7) may differ inside a batch.  Returns (records_in_batches, n_batches)."""
+    n = len(records)
+    if n == 0:
+        return np.zeros((0, 4), dtype=np.uint32), 0
+    base = (records[:, 0] & 0x7F).astype(np.int64)
+    n_levels = len(level_off) - 1
+    level = np.repeat(np.arange(n_levels, dtype=np.int64), np.diff(level_off).astype(np.int64))
+    live = base != OP_NOP
+    idx = np.nonzero(live)[0]
+    key = level[idx] * 128 + base[idx]
+    order = idx[np.argsort(key, kind="stable")]           # by level, then opcode, then sequence
+    key_sorted = level[order] * 128 + base[order]
+    # group boundaries
+    starts = np.nonzero(np.concatenate(([True], key_sorted[1:] != key_sorted[:-1])))[0]
+    sizes = np.diff(np.concatenate((starts, [len(order)])))
+    padded = (sizes + batch - 1) // batch * batch
+    out_start = np.concatenate(([0], np.cumsum(padded)))[:-1]
+    total = int(padded.sum())
+    out = np.empty((total, 4), dtype=np.uint32)
+    # padding: same opcode as the group, all operands on the trash slot
+    grp_op = base[order[starts]].astype(np.uint32)
+    pad_rec = np.empty((len(starts), 4), dtype=np.uint32)
+    pad_rec[:, 0] = grp_op | (np.uint32(trash_slot) << np.uint32(8))
+    pad_rec[:, 1] = trash_slot
+    pad_rec[:, 2] = trash_slot
+    pad_rec[:, 3] = trash_slot
+    out[:] = np.repeat(pad_rec, padded, axis=0)
+    grp_of = np.repeat(np.arange(len(starts)), sizes)
+    pos_in_grp = np.arange(len(order)) - starts[grp_of]
+    out[out_start[grp_of] + pos_in_grp] = records[order]
+    return out, total // batch
+
+
 def _sig_name(design: Design, s: int) -> str:
     if s >= design.n_signals:
         return "<temp %d>" % s

@@ -59,6 +59,8 @@ struct Tuning {
     int resident_block = 128;   // threads per CTA of the resident kernel
     int resident_tma = 1;       // stage the record stream with cp.async.bulk + mbarrier
     int resident_smem = 1;      // keep state in shared memory when it fits
+    int resident_word_bytes = 0;  // bytes of a lane column per thread (0: auto, 8, 4, 2, 1)
+    int resident_prefetch = 1;  // prefetch the fan-in rows two batches ahead
     int graph_min_steps = 2;    // mode 1: capture a graph when steps >= this
     int persist_unroll = 2;     // records per thread batch of the persistent level kernel
     int persist_hints = 1;      // honour the operand streaming hints (bit 31)
@@ -355,7 +357,6 @@ static int launch_persistent_t(const uint4 *recs, const int *d_level_off, int n_
 // either in global memory (L1/L2-resident across steps when small) or, when the whole slot
 // file of the CTA's columns fits, in shared memory for the entire run.
 // ------------------------------------------------------------------------------------------
-#define RU MCB_RESIDENT_UNROLL
 #define REC_CHUNK 512                      // records per staged chunk (8 KB)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {
@@ -386,64 +387,161 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
         :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// The word a thread owns is W = 8, 4, 2 or 1 bytes of a lane column: lanes never interact, so
+// a 64-lane word can be split among up to 8 threads.  Deep sequential circuits are latency
+// bound (one L2/HBM round trip per dependent batch), and narrower words multiply the number
+// of independent threads without adding traffic; wide runs use W = 8.
+// UNIFIED: scratch rows follow the persistent rows with the same stride (single-tile runs), so
+// a row address is one 32x32+64 multiply-add on a per-thread base that already includes the
+// thread's column; otherwise the plane is picked by comparing with n_persist.
+template <typename W, bool UNIFIED>
 struct GlobalCols {
-    View v;
-    long long col;
-    __device__ __forceinline__ uint64_t ld(uint32_t slot) const { return row(v, slot)[col]; }
-    __device__ __forceinline__ void st(uint32_t slot, uint64_t x) const { row(v, slot)[col] = x; }
+    char *base_p;                           // persist plane + this thread's column
+    char *base_s;                           // biased scratch plane + this thread's column
+    uint32_t stride_p, stride_s;            // bytes between rows
+    uint32_t n_persist;
+    __device__ __forceinline__ GlobalCols(const View &v, long long col) {
+        base_p = reinterpret_cast<char *>(v.persist) + col * (long long)sizeof(W);
+        base_s = reinterpret_cast<char *>(v.scratch_biased) + col * (long long)sizeof(W);
+        stride_p = (uint32_t)(v.pstride * 8);
+        stride_s = (uint32_t)(v.sstride * 8);
+        n_persist = v.n_persist;
+    }
+    __device__ __forceinline__ W *at(uint32_t slot) const {
+        if (UNIFIED) return reinterpret_cast<W *>(base_p + (unsigned long long)slot * stride_p);
+        return reinterpret_cast<W *>(slot < n_persist ? base_p + (unsigned long long)slot * stride_p
+                                                      : base_s + (unsigned long long)slot * stride_s);
+    }
+    __device__ __forceinline__ W ld(uint32_t slot) const { return *at(slot); }
+    __device__ __forceinline__ void st(uint32_t slot, W x) const { *at(slot) = x; }
+    // non-binding hint: safe even when an earlier batch still has to store to that row (a
+    // thread's own store is ordered before its later load of the same address)
+    __device__ __forceinline__ void prefetch(uint32_t slot) const {
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(at(slot)));
+    }
 };
 
 // state in shared memory: word(slot, thread) at smem[slot * blockDim.x + threadIdx.x]
+template <typename W>
 struct SmemCols {
-    uint64_t *base;
+    W *base;
     int stride;
-    __device__ __forceinline__ uint64_t ld(uint32_t slot) const { return base[slot * stride]; }
-    __device__ __forceinline__ void st(uint32_t slot, uint64_t x) const { base[slot * stride] = x; }
+    __device__ __forceinline__ W ld(uint32_t slot) const { return base[slot * stride]; }
+    __device__ __forceinline__ void st(uint32_t slot, W x) const { base[slot * stride] = x; }
+    __device__ __forceinline__ void prefetch(uint32_t) const {}
 };
 
-template <class Cols>
-__device__ __forceinline__ void run_batch(const uint4 *r4, const Cols &cols) {
-    uint4 r[RU];
-    uint64_t a[RU], b[RU], c[RU];
+template <typename W>
+__device__ __forceinline__ W apply_op_w(uint32_t op, W a, W b, W c) {
+    W r;
+    switch (op & 0x7f) {
+        case MCB_OP_BUF:  r = a; break;
+        case MCB_OP_AND:  r = a & b; break;
+        case MCB_OP_OR:   r = a | b; break;
+        case MCB_OP_XOR:  r = a ^ b; break;
+        case MCB_OP_ANDN: r = a & (W)~b; break;
+        case MCB_OP_MUX:  r = (a & b) | ((W)~a & c); break;
+        case MCB_OP_AND3: r = a & b & c; break;
+        case MCB_OP_OR3:  r = a | b | c; break;
+        case MCB_OP_XOR3: r = a ^ b ^ c; break;
+        case MCB_OP_MAJ:  r = (a & b) | (a & c) | (b & c); break;
+        default:          r = 0; break;
+    }
+    return (op & MCB_OP_NEG) ? (W)~r : r;
+}
+
+// One batch = U records of the SAME base opcode that the host proved independent (one level
+// of the netlist, grouped by opcode, padded with records that read and write a private trash
+// slot).  The opcode is decoded once per batch; inside, the U load / compute / store chains
+// are straight-line and branch-free, so the compiler interleaves them and a single warp keeps
+// U x 2..3 loads in flight.  Every load of a batch is issued before its first store.
+template <int OP, typename W>
+__device__ __forceinline__ W op_eval(W a, W b, W c) {
+    if (OP == MCB_OP_BUF) return a;
+    if (OP == MCB_OP_AND) return a & b;
+    if (OP == MCB_OP_OR) return a | b;
+    if (OP == MCB_OP_XOR) return a ^ b;
+    if (OP == MCB_OP_ANDN) return a & (W)~b;
+    if (OP == MCB_OP_MUX) return (a & b) | ((W)~a & c);
+    if (OP == MCB_OP_AND3) return a & b & c;
+    if (OP == MCB_OP_OR3) return a | b | c;
+    if (OP == MCB_OP_XOR3) return a ^ b ^ c;
+    return (a & b) | (a & c) | (b & c);                  // MCB_OP_MAJ
+}
+
+template <int OP, typename W, int U, class Cols>
+__device__ __forceinline__ void run_batch_op(const uint4 *r4, const Cols &cols) {
+    constexpr int ARITY = (OP == MCB_OP_BUF) ? 1 : (OP >= MCB_OP_MUX ? 3 : 2);
+    W a[U], b[U], c[U];
 #pragma unroll
-    for (int u = 0; u < RU; ++u) r[u] = r4[u];
-#pragma unroll
-    for (int u = 0; u < RU; ++u) {
-        const uint32_t op = r[u].x & 0x7f;
-        a[u] = b[u] = c[u] = 0;
-        if (op != MCB_OP_NOP) {
-            a[u] = cols.ld(r[u].y);
-            if (op != MCB_OP_BUF) b[u] = cols.ld(r[u].z);
-            if (op >= MCB_OP_MUX) c[u] = cols.ld(r[u].x >> 8);
-        }
+    for (int u = 0; u < U; ++u) {
+        const uint4 r = r4[u];
+        a[u] = cols.ld(r.y);
+        b[u] = (ARITY >= 2) ? cols.ld(r.z) : (W)0;
+        c[u] = (ARITY >= 3) ? cols.ld(r.x >> 8) : (W)0;
     }
 #pragma unroll
-    for (int u = 0; u < RU; ++u) {
-        const uint32_t op = r[u].x & 0xff;
-        if ((op & 0x7f) != MCB_OP_NOP) cols.st(r[u].w, apply_op(op, a[u], b[u], c[u]));
+    for (int u = 0; u < U; ++u) {
+        const uint4 r = r4[u];
+        const W neg = (W)0 - (W)((r.x >> 7) & 1u);       // all ones when the result is complemented
+        cols.st(r.w, (W)(op_eval<OP, W>(a[u], b[u], c[u]) ^ neg));
     }
 }
 
-template <bool TMA, bool SMEM_STATE>
+// Deep, narrow circuits are bound by one memory round trip per dependent batch; prefetching
+// the fan-in rows of the batch PF_DIST batches ahead turns that into L1 hits.
+#define PF_DIST 2
+
+template <typename W, int U, class Cols>
+__device__ __forceinline__ void prefetch_batch(const uint4 *r4, const Cols &cols) {
+    const bool three = (r4[0].x & 0x7f) >= MCB_OP_MUX;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint4 r = r4[u];
+        cols.prefetch(r.y);
+        cols.prefetch(r.z);
+        if (three) cols.prefetch(r.x >> 8);
+    }
+}
+
+template <typename W, int U, class Cols>
+__device__ __forceinline__ void run_batch(const uint4 *r4, const Cols &cols) {
+    switch (r4[0].x & 0x7f) {                            // uniform: one decode per batch
+        case MCB_OP_BUF:  run_batch_op<MCB_OP_BUF, W, U>(r4, cols); break;
+        case MCB_OP_AND:  run_batch_op<MCB_OP_AND, W, U>(r4, cols); break;
+        case MCB_OP_OR:   run_batch_op<MCB_OP_OR, W, U>(r4, cols); break;
+        case MCB_OP_XOR:  run_batch_op<MCB_OP_XOR, W, U>(r4, cols); break;
+        case MCB_OP_ANDN: run_batch_op<MCB_OP_ANDN, W, U>(r4, cols); break;
+        case MCB_OP_MUX:  run_batch_op<MCB_OP_MUX, W, U>(r4, cols); break;
+        case MCB_OP_AND3: run_batch_op<MCB_OP_AND3, W, U>(r4, cols); break;
+        case MCB_OP_OR3:  run_batch_op<MCB_OP_OR3, W, U>(r4, cols); break;
+        case MCB_OP_XOR3: run_batch_op<MCB_OP_XOR3, W, U>(r4, cols); break;
+        case MCB_OP_MAJ:  run_batch_op<MCB_OP_MAJ, W, U>(r4, cols); break;
+        default: break;                                   // a batch of NOPs
+    }
+}
+
+template <typename W, int U, bool TMA, bool SMEM_STATE, bool UNIFIED>
 __global__ void __launch_bounds__(256)
-k_run_resident(const uint4 *__restrict__ recs, int n_recs, View v, long long steps, int n_slots) {
+k_run_resident(const uint4 *__restrict__ recs, int n_recs, View v, long long steps, int n_slots,
+               int g_prefetch) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint4 *rbuf = reinterpret_cast<uint4 *>(smem_raw);                  // [2][REC_CHUNK]
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * REC_CHUNK * sizeof(uint4));
-    uint64_t *sstate = reinterpret_cast<uint64_t *>(smem_raw + 2 * REC_CHUNK * sizeof(uint4) + 128);
+    W *sstate = reinterpret_cast<W *>(smem_raw + 2 * REC_CHUNK * sizeof(uint4) + 128);
 
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = col < v.n_words;
+    const bool active = col < v.n_words * (long long)(8 / sizeof(W));
     const int tid = threadIdx.x;
     const int n_chunks = (n_recs + REC_CHUNK - 1) / REC_CHUNK;
     const long long total = steps * (long long)n_chunks;
 
-    GlobalCols gcols{v, col};
-    SmemCols scols{sstate + tid, (int)blockDim.x};
+    const GlobalCols<W, UNIFIED> gcols(v, col);
+    SmemCols<W> scols{sstate + tid, (int)blockDim.x};
 
     if (SMEM_STATE) {
         // bring this CTA's columns of every slot on chip once (coalesced: thread = column)
-        for (int s = 0; s < n_slots; ++s) scols.st(s, active ? gcols.ld(s) : 0ull);
+        for (int s = 0; s < n_slots; ++s) scols.st(s, active ? gcols.ld(s) : (W)0);
     }
     if (TMA) {
         if (tid == 0) {
@@ -479,9 +577,13 @@ k_run_resident(const uint4 *__restrict__ recs, int n_recs, View v, long long ste
         }
         const uint4 *rb = rbuf + buf * REC_CHUNK;
         if (active) {
-            for (int i = 0; i < cnt; i += RU) {
-                if (SMEM_STATE) run_batch(rb + i, scols);
-                else run_batch(rb + i, gcols);
+            const bool pf = !SMEM_STATE && g_prefetch;
+            if (pf)
+                for (int i = 0; i < PF_DIST * U && i < cnt; i += U) prefetch_batch<W, U>(rb + i, gcols);
+            for (int i = 0; i < cnt; i += U) {
+                if (pf && i + PF_DIST * U < cnt) prefetch_batch<W, U>(rb + i + PF_DIST * U, gcols);
+                if (SMEM_STATE) run_batch<W, U>(rb + i, scols);
+                else run_batch<W, U>(rb + i, gcols);
             }
         }
         __syncthreads();     // everyone is done with rbuf[buf] before it is refilled
@@ -492,44 +594,88 @@ k_run_resident(const uint4 *__restrict__ recs, int n_recs, View v, long long ste
     }
 }
 
-static int launch_resident(const uint4 *recs, int n_recs, const View &v, long long steps,
-                           int n_slots, cudaStream_t s) {
-    if (n_recs <= 0 || steps <= 0 || v.n_words <= 0) return 0;
-    if (n_recs % RU != 0) return fail(MCB_ERR_ARG, "resident stream must be padded to %d", RU);
+template <typename W, int U>
+static int launch_resident_wu(const uint4 *recs, int n_recs, const View &v, long long steps,
+                              int n_slots, cudaStream_t s) {
     const size_t fixed = 2 * REC_CHUNK * sizeof(uint4) + 128;
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     int max_smem = 0;
     CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    const long long cols = v.n_words * (long long)(8 / sizeof(W));
     int block = g_tune.resident_block;
     if (block > 256) block = 256;
     if (block < 32) block = 32;
     // shrink the CTA until the grid covers the SMs (few columns) ...
-    while (block > 32 && (v.n_words + block - 1) / block < sm_count()) block /= 2;
+    while (block > 32 && (cols + block - 1) / block < sm_count()) block /= 2;
     bool smem_state = false;
     size_t smem = fixed;
     if (g_tune.resident_smem) {
         // ... and keep the whole slot file of the CTA's columns on chip when it fits
         for (int b = block; b >= 32; b /= 2) {
-            size_t need = fixed + (size_t)n_slots * b * sizeof(uint64_t);
+            size_t need = fixed + (size_t)n_slots * b * sizeof(W);
             if (need <= (size_t)max_smem) { smem_state = true; smem = need; block = b; break; }
         }
     }
-    const long long grid = (v.n_words + block - 1) / block;
+    const long long grid = (cols + block - 1) / block;
     const bool tma = g_tune.resident_tma != 0;
-#define MCB_LR(T, S)                                                                       \
+    // one plane when the scratch rows simply continue the persistent rows
+    const bool unified = v.pstride * 8 < (1ll << 32) && v.sstride * 8 < (1ll << 32) &&
+                         (v.scratch_biased == nullptr ||
+                          (v.scratch_biased == v.persist && v.sstride == v.pstride));
+    if (v.pstride * 8 >= (1ll << 32) || v.sstride * 8 >= (1ll << 32))
+        return fail(MCB_ERR_ARG, "row stride of 4 GB or more is not supported by the resident kernel");
+#define MCB_LR(T, S, UF)                                                                   \
     do {                                                                                   \
-        CUDA_TRY(cudaFuncSetAttribute(k_run_resident<T, S>,                                \
+        CUDA_TRY(cudaFuncSetAttribute(k_run_resident<W, U, T, S, UF>,                      \
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_run_resident<T, S><<<(unsigned)grid, block, smem, s>>>(recs, n_recs, v, steps, n_slots); \
+        k_run_resident<W, U, T, S, UF><<<(unsigned)grid, block, smem, s>>>(recs, n_recs, v, steps, n_slots, \
+                                                                         g_tune.resident_prefetch); \
     } while (0)
-    if (tma && smem_state) MCB_LR(true, true);
-    else if (tma) MCB_LR(true, false);
-    else if (smem_state) MCB_LR(false, true);
-    else MCB_LR(false, false);
+    if (unified) {
+        if (tma && smem_state) MCB_LR(true, true, true);
+        else if (tma) MCB_LR(true, false, true);
+        else if (smem_state) MCB_LR(false, true, true);
+        else MCB_LR(false, false, true);
+    } else {
+        if (tma && smem_state) MCB_LR(true, true, false);
+        else if (tma) MCB_LR(true, false, false);
+        else if (smem_state) MCB_LR(false, true, false);
+        else MCB_LR(false, false, false);
+    }
 #undef MCB_LR
     LAUNCH_CHECK("k_run_resident");
     return 0;
+}
+
+template <typename W>
+static int launch_resident_w(int unroll, const uint4 *recs, int n_recs, const View &v,
+                             long long steps, int n_slots, cudaStream_t s) {
+    if (unroll == 8) return launch_resident_wu<W, 8>(recs, n_recs, v, steps, n_slots, s);
+    return launch_resident_wu<W, 4>(recs, n_recs, v, steps, n_slots, s);
+}
+
+static int launch_resident(const uint4 *recs, int n_recs, const View &v, long long steps,
+                           int n_slots, int unroll, int word_bytes, cudaStream_t s) {
+    if (n_recs <= 0 || steps <= 0 || v.n_words <= 0) return 0;
+    if (unroll != 4 && unroll != 8)
+        return fail(MCB_ERR_ARG, "resident batch size must be 4 or 8");
+    if (n_recs % unroll != 0) return fail(MCB_ERR_ARG, "resident stream must be padded to %d", unroll);
+    if (word_bytes == 0) word_bytes = g_tune.resident_word_bytes;
+    if (word_bytes == 0) {
+        // A narrower word multiplies the independent threads (latency hiding) but also the
+        // instructions per byte, so split only until every scheduler has ~3 warps.
+        const long long want = (long long)sm_count() * 32;   // at least a warp per SM
+        word_bytes = 8;
+        while (word_bytes > 1 && v.n_words * (8 / word_bytes) < want) word_bytes /= 2;
+    }
+    switch (word_bytes) {
+        case 8: return launch_resident_w<uint64_t>(unroll, recs, n_recs, v, steps, n_slots, s);
+        case 4: return launch_resident_w<uint32_t>(unroll, recs, n_recs, v, steps, n_slots, s);
+        case 2: return launch_resident_w<uint16_t>(unroll, recs, n_recs, v, steps, n_slots, s);
+        case 1: return launch_resident_w<uint8_t>(unroll, recs, n_recs, v, steps, n_slots, s);
+        default: return fail(MCB_ERR_ARG, "word_bytes must be 1, 2, 4 or 8");
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -690,6 +836,8 @@ int mcb_set_tuning(const char *key, int value) {
     else if (!strcmp(key, "resident_block")) p = &g_tune.resident_block;
     else if (!strcmp(key, "resident_tma")) p = &g_tune.resident_tma;
     else if (!strcmp(key, "resident_smem")) p = &g_tune.resident_smem;
+    else if (!strcmp(key, "resident_word_bytes")) p = &g_tune.resident_word_bytes;
+    else if (!strcmp(key, "resident_prefetch")) p = &g_tune.resident_prefetch;
     else if (!strcmp(key, "graph_min_steps")) p = &g_tune.graph_min_steps;
     else if (!strcmp(key, "persist_unroll")) p = &g_tune.persist_unroll;
     else if (!strcmp(key, "persist_hints")) p = &g_tune.persist_hints;
@@ -755,11 +903,14 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
     cudaStream_t s = (cudaStream_t)stream;
     const View v = make_view(st);
     const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
+    const int unroll = (mode >> 8) & 0xff, word_bytes = (mode >> 16) & 0xff;
+    mode &= 0xff;
     if (mode == 0) {
+        const int u = unroll ? unroll : MCB_RESIDENT_UNROLL;
         for (int l = 0; l <= n_levels; ++l)
-            if (h_level_off[l] % RU)
-                return fail(MCB_ERR_ARG, "mode 0 needs every level padded to %d records", RU);
-        return launch_resident(recs, h_level_off[n_levels], v, steps, st->n_slots, s);
+            if (h_level_off[l] % u)
+                return fail(MCB_ERR_ARG, "mode 0 needs every segment padded to %d records", u);
+        return launch_resident(recs, h_level_off[n_levels], v, steps, st->n_slots, u, word_bytes, s);
     }
     if (mode != 1) return fail(MCB_ERR_ARG, "unknown mode %d", mode);
     if (steps < g_tune.graph_min_steps || s == nullptr) {

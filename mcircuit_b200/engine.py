@@ -71,7 +71,8 @@ class B200Engine(Executor):
     def __init__(self, root, burst_size=500, map_pins=True, *, lanes=64, device=None,
                  keep="auto", observe: Sequence[str] = (), tile_words: Optional[int] = None,
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
-                 memory_budget: Optional[int] = None, back_edges="auto"):
+                 memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
+                 resident_word_bytes=0):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -95,7 +96,11 @@ class B200Engine(Executor):
             program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges)
         self.program = program
         self.keep = keep
-        P, S = program.n_persist, program.n_scratch
+        # one extra scratch row that padding records of the resident kernel read and write
+        P, S = program.n_persist, program.n_scratch + 1
+        self.trash_slot = P + S - 1
+        if self.trash_slot >= compiler.IN2_LIMIT:
+            raise compiler.CircuitError("too many slots for the resident kernel's padding records")
 
         # ---- execution mode -------------------------------------------------------------------
         avg_level = program.n_ops / max(1, program.n_levels)
@@ -136,7 +141,11 @@ class B200Engine(Executor):
             self._scratch = self.rt.zeros_words(S * self.scratch_stride + _ALIGN_WORDS)
         self._d_records = self.rt.to_device(program.records)
         self._h_level_off = np.ascontiguousarray(program.level_off, dtype=np.int32)
-        self._resident = None      # (d_records_padded, h_level_off_padded), built on first use
+        self._resident = None      # (d_records in batches, h_level_off), built on first use
+        # resident kernel: records per batch (4, 8, 16) and bytes of a lane word per thread (0 = auto)
+        self.resident_batch = int(resident_batch) if resident_batch else 8
+        self.resident_word_bytes = int(resident_word_bytes)
+        self.resident_batches = None
         self._whole = self._state_for(0, self.words, whole=True)
         self._slot_cache: Dict[str, object] = {}
         self.steps_done = 0
@@ -149,7 +158,7 @@ class B200Engine(Executor):
     # state views
     # ------------------------------------------------------------------------------------------
     def _state_for(self, col0, n_words, whole=False):
-        P, S = self.program.n_persist, self.program.n_scratch
+        P, S = self.program.n_persist, self.program.n_scratch + 1
         if self.n_tiles == 1:
             return self.rt.make_state(self._plane, self.stride, self._plane, self.stride, P, P + S,
                                       n_words, col_offset=col0,
@@ -208,10 +217,15 @@ class B200Engine(Executor):
                                    self._state_for(c0, n), steps)
         elif self.mode == "resident":
             if self._resident is None:
-                rec, off = pad_levels(self.program.records, self.program.level_off)
-                self._resident = (self.rt.to_device(rec), off)
+                rec, n_batches = compiler.schedule_batches(self.program.records, self.program.level_off,
+                                                           self.trash_slot, self.resident_batch)
+                off = np.array([0, len(rec)], dtype=np.int32)
+                self._resident = (self.rt.to_device(rec) if len(rec) else None, off)
+                self.resident_batches = n_batches
             d_rec, off = self._resident
-            self.rt.run(d_rec, off, self.program.n_levels, self._state_for(c0, n), steps, MODE_RESIDENT)
+            if d_rec is not None:
+                self.rt.run(d_rec, off, 1, self._state_for(c0, n), steps,
+                            MODE_RESIDENT | (self.resident_batch << 8) | (self.resident_word_bytes << 16))
         else:
             self.rt.run(self._d_records, self._h_level_off, self.program.n_levels,
                         self._state_for(c0, n), steps, MODE_LEVELS)

@@ -145,13 +145,15 @@ class CpuRuntime:
         self._level(d_records[:n].astype(np.int64), st)
 
     def run(self, d_records, h_level_off, n_levels, st, steps, mode):
+        batch = ((mode >> 8) & 0xFF) or 4
+        mode &= 0xFF
         if mode == 0:
-            assert all(int(x) % 4 == 0 for x in h_level_off), "resident stream must be padded"
-            # batches of 4 records, loads before stores - exactly the kernel's hazard model
+            assert all(int(x) % batch == 0 for x in h_level_off), "resident stream must be padded"
+            # batches of records, loads before stores - exactly the kernel's hazard model
             recs = d_records.astype(np.int64)
             for _ in range(int(steps)):
-                for i in range(0, int(h_level_off[n_levels]), 4):
-                    self._level(recs[i:i + 4], st)
+                for i in range(0, int(h_level_off[n_levels]), batch):
+                    self._level(recs[i:i + batch], st)
         else:
             for _ in range(int(steps)):
                 self.eval_levels(d_records, h_level_off, 0, n_levels, st)

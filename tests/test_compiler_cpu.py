@@ -287,3 +287,33 @@ def test_streaming_hints_shape():
     lv5 = slice(p.level_off[5], p.level_off[6])
     assert not (h[lv5, 1] >> 31).any()                                   # in0 comes from level 4
     assert (h[lv5, 2] >> 31).mean() > 0.5                                # in1 mostly from far back
+
+
+@pytest.mark.parametrize("batch", [4, 8])
+def test_batch_schedule_hazards_and_results(batch):
+    """schedule_batches: every record placed exactly once, batches are homogeneous in opcode,
+    nothing inside a batch reads what the batch writes (except in place), and the engine
+    (numpy double, loads-before-stores per batch) still matches the oracle."""
+    root = circuits.lfsr_pipeline(MD, 3, 8, 10, taps=(7, 5, 1, 0))
+    p = compiler.compile_circuit(root, keep="ports")
+    trash = p.n_slots
+    rec, nb = compiler.schedule_batches(p.records, p.level_off, trash, batch)
+    assert len(rec) == nb * batch
+    real = rec[rec[:, 3] != trash]
+    assert len(real) == p.n_ops
+    assert sorted(map(tuple, real.tolist())) == sorted(map(tuple, p.records.tolist()))
+    for b in range(nb):
+        grp = rec[b * batch:(b + 1) * batch].astype(np.int64)
+        assert len(set((grp[:, 0] & 0x7F).tolist())) == 1                # one base opcode
+        grp = grp[grp[:, 3] != trash]
+        writes = {int(r[3]): k for k, r in enumerate(grp)}
+        assert len(writes) == len(grp)
+        for k, r in enumerate(grp):
+            ar = compiler.OP_ARITY[int(r[0] & 0x7F)]
+            for s_ in [r[1], r[2], r[0] >> 8][:ar]:
+                assert int(s_) not in writes or writes[int(s_)] == k      # only an in-place read
+    probes = [f"/tap{n}/pin" for n in range(3)] + ["/pipe_out/pin"]
+    pokes = [(f"/l{n}_q{b}/out", (n + b) & 1) for n in range(3) for b in range(8)]
+    compare_engine_to_oracle(lambda M: circuits.lfsr_pipeline(M, 3, 8, 10, taps=(7, 5, 1, 0)),
+                             lambda r, bs, lanes: engine_factory("resident", "ports", resident_batch=batch)(r, bs, lanes),
+                             lanes=64, steps=30, probes=probes, pokes=pokes)

@@ -258,3 +258,21 @@ def test_gpu_persistent_level_kernel_variants(cuda_rt, unroll, hints):
     finally:
         cuda_rt.set_tuning("persist_unroll", 2)
         cuda_rt.set_tuning("persist_hints", 1)
+
+
+@pytest.mark.parametrize("word_bytes", [1, 2, 4, 8])
+@pytest.mark.parametrize("batch", [4, 8])
+def test_gpu_resident_word_and_batch_variants(word_bytes, batch):
+    """The resident kernel with a lane word split among 8/4/2/1 threads and 4/8-record
+    homogeneous batches: same results as the oracle."""
+    for case in TRACES[:10] + TRACES[-6:]:
+        run_trace_case(case, gpu_factory("resident", "all", True, resident_word_bytes=word_bytes,
+                                         resident_batch=batch))
+    root, probes = circuits.random_circuit(MD, 777, n_nodes=30)
+    d = compiler.flatten(root)
+    lane_inputs = [(p, d.pin_width[d.find_pin(p)]) for p in ("/in0/pin", "/in1/pin")]
+    compare_engine_to_oracle(lambda M: circuits.random_circuit(M, 777, n_nodes=30),
+                             lambda r, bs, n: gpu_factory("resident", "all", True, resident_word_bytes=word_bytes,
+                                                          resident_batch=batch)(r, bs, n),
+                             lanes=64 * 5, steps=9, probes=probes,
+                             lane_inputs=lane_inputs, seed=5)
