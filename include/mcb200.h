@@ -130,6 +130,11 @@ int mcb_pack(const uint64_t *d_values, int width, const int32_t *d_slots,
 int mcb_unpack(uint64_t *d_values, int width, const int32_t *d_slots,
                const mcb_state *st, void *stream);
 
+/* Waveform capture (observability after the path; the reference can only peek one pin of one
+ * instance, core/simulator.py:285-287): d_dst[i * dst_stride + j] = word(d_slots[i], j).     */
+int mcb_capture_rows(const int32_t *d_slots, int n, const mcb_state *st, uint64_t *d_dst,
+                     int64_t dst_stride, void *stream);
+
 /* Strided host<->device copy of `rows` row segments of `width_bytes` (pinned host memory for
  * true asynchrony): the bulk form of set/get_pin_state for whole lane tiles, so a tile's
  * stimulus upload and result download overlap the evaluation of its neighbours.

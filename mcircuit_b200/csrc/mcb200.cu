@@ -769,6 +769,14 @@ k_fill_rows(const int *__restrict__ slots, const uint64_t *__restrict__ values, 
     for (int i = blockIdx.y; i < n; i += gridDim.y) row(v, (uint32_t)slots[i])[j] = values[i];
 }
 
+// waveform capture: copy the current rows of `n` slots into a sample buffer
+__global__ void __launch_bounds__(256)
+k_capture(const int *__restrict__ slots, int n, View v, uint64_t *__restrict__ dst, long long dst_stride) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= v.n_words) return;
+    for (int i = blockIdx.y; i < n; i += gridDim.y) dst[(long long)i * dst_stride + j] = row(v, (uint32_t)slots[i])[j];
+}
+
 // 64 lanes (two per thread of a warp) -> one word per bit plane, by ballot
 __global__ void __launch_bounds__(256)
 k_pack(const uint64_t *__restrict__ values, int width, const int *__restrict__ slots, View v) {
@@ -1043,6 +1051,19 @@ int mcb_fill_rows(const int32_t *d_slots, const uint64_t *d_values, int n, const
     k_fill_rows<<<row_grid(st->n_words, n), 256, 0, (cudaStream_t)stream>>>(d_slots, d_values, n,
                                                                               make_view(st));
     LAUNCH_CHECK("k_fill_rows");
+    return 0;
+}
+
+int mcb_capture_rows(const int32_t *d_slots, int n, const mcb_state *st, uint64_t *d_dst,
+                     int64_t dst_stride, void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (n < 0 || (n > 0 && (!d_slots || !d_dst)) || dst_stride < st->n_words)
+        return fail(MCB_ERR_ARG, "bad capture arguments");
+    if (n == 0 || st->n_words == 0) return 0;
+    k_capture<<<row_grid(st->n_words, n), 256, 0, (cudaStream_t)stream>>>(d_slots, n, make_view(st), d_dst,
+                                                                            dst_stride);
+    LAUNCH_CHECK("k_capture");
     return 0;
 }
 

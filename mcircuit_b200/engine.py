@@ -352,6 +352,8 @@ class B200Engine(Executor):
     # ---- stimulus / signatures --------------------------------------------------------------------------
     def input_pins(self) -> List[str]:
         """Root-level IN ports, in child order."""
+        if self.program.design is None:                     # program loaded from a cache
+            return list(self.program.ports_in)
         d = self.program.design
         out = []
         for name, child in d.top.children.items():
@@ -362,6 +364,8 @@ class B200Engine(Executor):
         return out
 
     def output_pins(self) -> List[str]:
+        if self.program.design is None:
+            return list(self.program.ports_out)
         d = self.program.design
         out = []
         for name, child in d.top.children.items():
@@ -498,6 +502,30 @@ class B200Engine(Executor):
 
     def toggle_counts_device(self):
         return self._toggle["counts"][: self._toggle["n"]]
+
+    # ---- waveform capture ---------------------------------------------------------------------------------
+    def capture(self, pins: Sequence[str], steps: int, every: int = 1) -> np.ndarray:
+        """Run ``steps`` steps and sample every bit of ``pins`` after each ``every``-th step.
+        Samples stay on the device until the end.  Returns uint64[samples, n_bits, words]."""
+        slots = self._flat_slots(pins)
+        n = len(slots)
+        n_samples = steps // every
+        d_slots = self.rt.to_device(np.asarray(slots or [0], dtype=np.int32))
+        buf = self.rt.zeros_words(max(1, n_samples * n * self.stride))
+        k = 0
+        for _ in range(n_samples):
+            self.run(every)
+            if n:
+                self.rt.capture_rows(d_slots, n, self._whole, buf, k * n * self.stride, self.stride)
+            k += 1
+        if steps - n_samples * every:
+            self.run(steps - n_samples * every)
+        host = self.rt.to_host_u64(buf)[: n_samples * n * self.stride]
+        return host.reshape(n_samples, max(n, 1), self.stride)[:, :n, :self.words].copy() if n else \
+            np.zeros((n_samples, 0, self.words), dtype=np.uint64)
+
+    def pin_widths(self, pins: Sequence[str]) -> List[int]:
+        return [self._slots_of(p)[1] for p in pins]
 
     # ---- accounting ----------------------------------------------------------------------------------------
     def synchronize(self):

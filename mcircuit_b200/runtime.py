@@ -57,6 +57,7 @@ _PROTOTYPES = [
     ("mcb_fill_rows", c_int, [c_void_p, c_void_p, c_int, POINTER(McbState), c_void_p]),
     ("mcb_pack", c_int, [c_void_p, c_int, c_void_p, POINTER(McbState), c_void_p]),
     ("mcb_unpack", c_int, [c_void_p, c_int, c_void_p, POINTER(McbState), c_void_p]),
+    ("mcb_capture_rows", c_int, [c_void_p, c_int, POINTER(McbState), c_void_p, c_int64, c_void_p]),
     ("mcb_copy2d", c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     ("mcb_set_tuning", c_int, [c_char_p, c_int]),
     ("mcb_launch_count", c_int64, [c_int]),
@@ -217,6 +218,12 @@ class CudaRuntime:
         with self.torch.cuda.device(self.device):
             self._check(self.lib.mcb_unpack(
                 d_values.data_ptr(), int(width), d_slots.data_ptr(), ctypes.byref(st), self._stream()))
+
+    def capture_rows(self, d_slots, n, st: McbState, d_dst, dst_word_offset, dst_stride):
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.mcb_capture_rows(d_slots.data_ptr(), int(n), ctypes.byref(st),
+                                                  c_void_p(self.ptr(d_dst, dst_word_offset)), int(dst_stride),
+                                                  self._stream()))
 
     def copy2d(self, dst_ptr, dst_pitch, src_ptr, src_pitch, width_bytes, rows, h2d: bool, stream=None):
         st = c_void_p(stream.cuda_stream) if stream is not None else self._stream()

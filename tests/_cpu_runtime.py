@@ -216,6 +216,13 @@ class CpuRuntime:
         d_values[: st.n_words * 64] = out
         self._launches += 1
 
+    def capture_rows(self, d_slots, n, st, d_dst, dst_word_offset, dst_stride):
+        rows = st.read(d_slots[:n])
+        for i in range(n):
+            o = dst_word_offset + i * dst_stride
+            d_dst[o:o + st.n_words] = rows[i]
+        self._launches += 1
+
     def set_tuning(self, key, value):
         return 0
 

@@ -276,3 +276,24 @@ def test_gpu_resident_word_and_batch_variants(word_bytes, batch):
                                                           resident_batch=batch)(r, bs, n),
                              lanes=64 * 5, steps=9, probes=probes,
                              lane_inputs=lane_inputs, seed=5)
+
+
+def test_gpu_capture_waveform_and_program_cache(tmp_path):
+    from mcircuit_b200 import netlist_io, waveform
+    eng = B200Engine(circuits.counter_circuit(MD), 1, True, lanes=128)
+    pins = ["/clk/out", "/r/out"]
+    samples = eng.capture(pins, 8)
+    clk, r = waveform.lane_values(samples, eng.pin_widths(pins), lane=70)
+    assert clk == [1, 0, 1, 0, 1, 0, 1, 0] and r == [1, 1, 0, 0, 1, 1, 0, 0]
+    root = circuits.random_dag(MD, n_gates=800, depth=16, n_inputs=32, seed=2)
+    prog = compiler.compile_circuit(root, keep="ports")
+    netlist_io.save_program(prog, tmp_path / "p.npz")
+    cached = netlist_io.load_program(tmp_path / "p.npz")
+    a = B200Engine(root, 1, True, lanes=64 * 40, keep="ports", mode="levels", program=prog)
+    b = B200Engine(None, 1, True, lanes=64 * 40, mode="levels", program=cached)
+    for e in (a, b):
+        e.randomize_inputs()
+        e.step()
+    pa, ca = a.signature()
+    pb, cb = b.signature()
+    assert np.array_equal(pa, pb) and np.array_equal(ca, cb)

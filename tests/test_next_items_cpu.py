@@ -1,0 +1,121 @@
+"""not-gpu: the SURVEY 8f "next" items - headless Schematic.reconstruct composites, the
+netlist file format / compiled-program cache and waveform capture - on the numpy test double."""
+import json
+
+import numpy as np
+import pytest
+
+import mcircuit_b200.core.descriptors as MD
+from _cpu_runtime import CpuRuntime
+from mcircuit_b200 import circuits, compiler, netlist_io, schematic, waveform
+from mcircuit_b200.engine import B200Engine
+from oracle import restate
+
+
+def _gui_full_adder(M=MD):
+    """What the GUI would hold for a 1-bit full adder drawn with LIBRARY elements (app.py:575-589)."""
+    ein, eout = M.ExposedPin(M.ExposedPin.IN), M.ExposedPin(M.ExposedPin.OUT)
+    elements = [("input0", ein), ("input1", ein), ("input2", ein), ("xor0", M.Gate(M.Gate.XOR)),
+                ("xor1", M.Gate(M.Gate.XOR)), ("and0", M.Gate(M.Gate.AND)), ("and1", M.Gate(M.Gate.AND)),
+                ("or0", M.Gate(M.Gate.OR)), ("output0", eout), ("output1", eout), ("nand_unused", M.Gate(M.Gate.AND, negated=True))]
+    nets = [
+        [("input0", "pin"), ("xor0", "in0"), ("and1", "in0")],
+        [("input1", "pin"), ("xor0", "in1"), ("and1", "in1")],
+        [("input2", "pin"), ("xor1", "in1"), ("and0", "in1")],
+        [("xor0", "out"), ("xor1", "in0"), ("and0", "in0")],
+        [("xor1", "out"), ("output0", "pin")],
+        [("and0", "out"), ("or0", "in0")],
+        [("and1", "out"), ("or0", "in1")],
+        [("or0", "out"), ("output1", "pin")],
+    ]
+    return elements, nets
+
+
+def test_schematic_reconstruct_shape_and_result():
+    elements, nets = _gui_full_adder()
+    s = schematic.reconstruct(elements, nets)
+    assert list(s.graph.nodes) == [n for n, _ in elements]          # children in element order
+    assert ("input0", "pin", "xor0", "in0") in s.connections and ("or0", "out", "output1", "pin") in s.connections
+    assert len(s.connections) == 12
+    # sources outer, dests inner: first edges come from input0 in dest order
+    assert list(s.graph.edges)[:2] == [("xor0", "input0"), ("xor0", "input1")] or \
+        list(s.graph.predecessors("input0")) == ["xor0", "and1"]
+    # runs through the engine exactly like app.py:732 does: JIT(s, 500, True)
+    eng = B200Engine(s, 500, True, runtime=CpuRuntime())
+    ora = restate.RestatedJIT(s, 500, True)
+    for a in (0, 1):
+        for b in (0, 1):
+            for c in (0, 1):
+                for sim in (eng, ora):
+                    sim.set_pin_state("/input0/pin", a)
+                    sim.set_pin_state("/input1/pin", b)
+                    sim.set_pin_state("/input2/pin", c)
+                    sim.step()
+                assert eng.get_pin_state("/output0/pin") == ora.get_pin_state("/output0/pin") == (a ^ b ^ c)
+                assert eng.get_pin_state("/output1/pin") == ora.get_pin_state("/output1/pin") == (a + b + c) // 2
+
+
+def test_schematic_matches_live_reference_connect_order(reference):
+    D, S = reference
+    el_ref, nets = _gui_full_adder(D)
+    s_ref = schematic.reconstruct(el_ref, nets, M=D)
+    s_own = schematic.reconstruct(*_gui_full_adder(MD))
+    emits_ref = [v[1] for k, v in S.iter_simulation_topology(s_ref) if k == "emit"]
+    d = compiler.flatten(s_own)
+    assert emits_ref == [d.leaf_path[a] for k, a in d.schedule if k == 0]
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_netlist_json_roundtrip_preserves_order_and_results(tmp_path, seed):
+    root, probes = circuits.random_circuit(MD, seed, n_nodes=20,
+                                           primitives=("Gate", "Not", "Constant", "Clock", "Counter", "Adder", "Register"))
+    path = tmp_path / "n.json"
+    netlist_io.save(root, path)
+    back = netlist_io.load(path)
+    a, b = compiler.flatten(root), compiler.flatten(back)
+    assert list(a.iter_pins()) == list(b.iter_pins())
+    assert a.schedule == b.schedule or [x for x in a.schedule if x[0] == 0] == [x for x in b.schedule if x[0] == 0]
+    assert [a.leaf_path[x] for k, x in a.schedule if k == 0] == [b.leaf_path[x] for k, x in b.schedule if k == 0]
+    assert np.array_equal(a.pin_src, b.pin_src)
+    pa, pb = compiler.compile_design(a), compiler.compile_design(b)
+    assert np.array_equal(pa.records, pb.records) and np.array_equal(pa.level_off, pb.level_off)
+    json.loads(path.read_text())["mcircuit_b200_netlist"] == 1
+
+
+def test_netlist_json_shares_instanced_descriptors(tmp_path):
+    root = circuits.raw_counter(MD, 2, 1)
+    d = netlist_io.to_dict(root)
+    assert sum(1 for x in d["defs"] if x["type"] == "Composite") == 6      # adder clock sr d latch main
+    back = netlist_io.from_dict(d)
+    assert back.get_child("b1") is back.get_child("b2")                    # still one object, two names
+
+
+def test_program_cache_runs_without_design(tmp_path):
+    root = circuits.random_dag(MD, n_gates=800, depth=16, n_inputs=32, seed=2)
+    prog = compiler.compile_circuit(root, keep="ports")
+    path = tmp_path / "prog.npz"
+    netlist_io.save_program(prog, path)
+    cached = netlist_io.load_program(path)
+    a = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), keep="ports", mode="levels", program=prog)
+    b = B200Engine(None, 1, True, lanes=128, runtime=CpuRuntime(), mode="levels", program=cached)
+    for e in (a, b):
+        e.randomize_inputs()
+        e.step()
+    assert b.input_pins() == a.input_pins() and b.output_pins() == a.output_pins()
+    for p in a.output_pins():
+        assert np.array_equal(a.get_pin_planes(p), b.get_pin_planes(p))
+    with pytest.raises(KeyError):
+        b.get_pin_state("/g3_7/out")                                        # not retained -> not in the cache
+
+
+def test_capture_and_vcd():
+    eng = B200Engine(circuits.counter_circuit(MD), 1, True, lanes=128, runtime=CpuRuntime())
+    pins = ["/clk/out", "/r/out"]
+    samples = eng.capture(pins, 8)
+    assert samples.shape == (8, 17, 2)
+    clk, r = waveform.lane_values(samples, eng.pin_widths(pins), lane=70)
+    assert clk == [1, 0, 1, 0, 1, 0, 1, 0] and r == [1, 1, 0, 0, 1, 1, 0, 0]
+    vcd = waveform.to_vcd(pins, eng.pin_widths(pins), samples)
+    assert "$var wire 1 ! clk.out $end" in vcd and '$var wire 16 " r.out $end' in vcd
+    assert '#0\n1!\nb1 "' in vcd and '#2\n1!\nb0 "' in vcd
+    assert eng.steps_done == 8
