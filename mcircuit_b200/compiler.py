@@ -235,7 +235,13 @@ def flatten(root, map_pins: bool = True) -> Design:
         if g is None:
             g = {}
             for conn in node.connections:      # set order; stable within this process
-                g.setdefault(conn[0].split("/")[0], []).append(conn)
+                c0 = conn[0]
+                key = c0 if "/" not in c0 else c0.split("/")[0]
+                lst = g.get(key)
+                if lst is None:
+                    g[key] = [conn]
+                else:
+                    lst.append(conn)
             grouped[id(node)] = g
             keepalive.append(node)
         return g
@@ -247,7 +253,15 @@ def flatten(root, map_pins: bool = True) -> Design:
             postorder[id(node)] = p
         return p
 
+    leaf_table, leaf_pin_base = d.leaf_table, d.leaf_pin_base
+
     def resolve(inst: _Instance, cname: str, pname: str) -> int:
+        leaf = inst.children.get(cname)                   # fast path: a direct leaf child
+        if leaf.__class__ is int:
+            k = leaf_table[leaf].index.get(pname)
+            if k is None:
+                raise KeyError(inst.path + cname + "/" + pname)
+            return leaf_pin_base[leaf] + k
         here = inst
         parts = cname.split("/")
         for part in parts[:-1]:
@@ -263,55 +277,69 @@ def flatten(root, map_pins: bool = True) -> Design:
         return d.leaf_pin_base[leaf] + k
 
     # ---- pass 2: connections in the reference's enumeration order (simulator.py:28-38) --
-    conn_index: Dict[Tuple[int, tuple], int] = {}
+    conn_first: Dict[int, Dict[str, int]] = {}     # id(instance) -> child name -> first conn index
+    conn_src, conn_dst = d.conn_src, d.conn_dst
 
     def walk_conns(inst: _Instance):
         node = inst.node
         groups = groups_of(node)
+        first = conn_first[id(inst)] = {}
+        children = inst.children
         for name in node.graph.nodes:
-            child = inst.children[name]
-            if isinstance(child, _Instance):
+            child = children[name]
+            if child.__class__ is _Instance:
                 walk_conns(child)
-            for conn in groups.get(name, ()):
-                conn_index[(id(inst), conn)] = len(d.conn_src)
-                d.conn_src.append(resolve(inst, conn[0], conn[1]))
-                d.conn_dst.append(resolve(inst, conn[2], conn[3]))
+            grp = groups.get(name)
+            if grp:
+                first[name] = len(conn_src)
+                for conn in grp:
+                    conn_src.append(resolve(inst, conn[0], conn[1]))
+                    conn_dst.append(resolve(inst, conn[2], conn[3]))
 
     walk_conns(d.top)
 
     # ---- pass 3: the schedule (simulator.py:41-53) ---------------------------------------
     sched = d.schedule
 
+    want_props = not d.map_pins      # aliased globals make every propagate a self-copy (Q7)
+
     def walk_topo(inst: _Instance):
         node = inst.node
         groups = groups_of(node)
+        first = conn_first[id(inst)]
+        children = inst.children
         for name in post_of(node):
-            child = inst.children[name]
-            if isinstance(child, _Instance):
+            child = children[name]
+            if child.__class__ is _Instance:
                 walk_topo(child)
             else:
                 sched.append((_SCHED_EMIT, child))
-            for conn in groups.get(name, ()):
-                sched.append((_SCHED_PROP, conn_index[(id(inst), conn)]))
+            if want_props:
+                grp = groups.get(name)
+                if grp:
+                    k0 = first[name]
+                    for k in range(len(grp)):
+                        sched.append((_SCHED_PROP, k0 + k))
 
     walk_topo(d.top)
 
     # ---- pass 4: aliasing (simulator.py:56-74) -------------------------------------------
     n_pins = len(d.pin_width)
-    driver = np.full(n_pins, -1, dtype=np.int64)
-    for s, t in zip(d.conn_src, d.conn_dst):
-        if driver[t] != -1 and driver[t] != s:
+    drv = [-1] * n_pins
+    for s_, t in zip(conn_src, conn_dst):
+        if drv[t] != -1 and drv[t] != s_:
             raise CircuitError(
                 "pin %s is driven by both %s and %s; the reference keeps whichever the set "
                 "iteration yields last (hash-seed dependent), so this is rejected"
-                % (d.pin_path(t), d.pin_path(int(driver[t])), d.pin_path(s)))
-        driver[t] = s
-    src = np.full(n_pins, -1, dtype=np.int64)
-    state = np.zeros(n_pins, dtype=np.int8)       # 0 unknown, 1 on stack, 2 done
-    drv = driver.tolist()
+                % (d.pin_path(t), d.pin_path(drv[t]), d.pin_path(s_)))
+        drv[t] = s_
+    state = bytearray(n_pins)                      # 0 unknown, 1 on the current chain, 2 done
     root_of = list(range(n_pins))
     for p in range(n_pins):
         if state[p] == 2:
+            continue
+        if drv[p] == -1:
+            state[p] = 2
             continue
         chain = []
         cur = p
@@ -328,36 +356,38 @@ def flatten(root, map_pins: bool = True) -> Design:
         for c in chain:
             root_of[c] = r
             state[c] = 2
-    for p in range(n_pins):
-        if drv[p] != -1:
-            src[p] = root_of[p]
-    d.pin_src = src
+    roots = np.asarray(root_of, dtype=np.int64)
+    driven = np.asarray(drv, dtype=np.int64) != -1
+    d.pin_src = np.where(driven, roots, -1)
 
     # ---- nets ----------------------------------------------------------------------------
+    pw = np.asarray(d.pin_width, dtype=np.int64)
     if d.map_pins:
-        net_of_root: Dict[int, int] = {}
-        pin_net = np.empty(n_pins, dtype=np.int64)
-        for p in range(n_pins):
-            r = root_of[p]
-            n = net_of_root.get(r)
-            if n is None:
-                n = len(d.net_width)
-                net_of_root[r] = n
-                d.net_width.append(d.pin_width[r])
-            if d.pin_width[p] != d.net_width[n]:
-                raise CircuitError(
-                    "width mismatch: %s is %d bits but its source %s is %d bits (the "
-                    "reference fails in llvmlite with a type error here)"
-                    % (d.pin_path(p), d.pin_width[p], d.pin_path(r), d.net_width[n]))
-            pin_net[p] = n
+        # net ids in order of first appearance of their root among the pins
+        uniq, first_idx, inverse = np.unique(roots, return_index=True, return_inverse=True)
+        rank = np.empty(len(uniq), dtype=np.int64)
+        rank[np.argsort(first_idx, kind="stable")] = np.arange(len(uniq))
+        pin_net = rank[inverse]
+        net_root = np.empty(len(uniq), dtype=np.int64)
+        net_root[rank] = uniq
+        net_w = pw[net_root]
+        bad = np.nonzero(pw != net_w[pin_net])[0]
+        if len(bad):
+            pb = int(bad[0])
+            rb = int(roots[pb])
+            raise CircuitError(
+                "width mismatch: %s is %d bits but its source %s is %d bits (the "
+                "reference fails in llvmlite with a type error here)"
+                % (d.pin_path(pb), d.pin_width[pb], d.pin_path(rb), d.pin_width[rb]))
         d.pin_net = pin_net
+        d.net_width = net_w.tolist()
     else:
         d.pin_net = np.arange(n_pins, dtype=np.int64)
         d.net_width = list(d.pin_width)
-        for s, t in zip(d.conn_src, d.conn_dst):
-            if d.pin_width[s] != d.pin_width[t]:
+        for s_, t in zip(conn_src, conn_dst):
+            if d.pin_width[s_] != d.pin_width[t]:
                 raise CircuitError("width mismatch: %s (%d) -> %s (%d)" % (
-                    d.pin_path(s), d.pin_width[s], d.pin_path(t), d.pin_width[t]))
+                    d.pin_path(s_), d.pin_width[s_], d.pin_path(t), d.pin_width[t]))
     widths = np.asarray(d.net_width, dtype=np.int64)
     d.net_sig = np.concatenate(([0], np.cumsum(widths)))[:-1] if len(widths) else np.zeros(0, np.int64)
     d.n_signals = int(widths.sum())
