@@ -93,15 +93,22 @@ int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void 
 int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
             const mcb_state *st, int64_t steps, int mode, void *stream);
 
-/* K1p - all levels of one lane tile in ONE cooperative launch with a grid barrier between
- * levels (same replaced interface as mcb_eval_levels / mcb_run).  Meant for small tiles
- * (<= 512 lane words) whose per-level rows stay in L2 from one level to the next.  The record
- * stream may carry operand hints: bit 31 of in0 / in1 = "producer is two or more levels back:
- * stream it through L2"; slot numbers are the low 31 bits.  `d_level_off` is the device copy
- * of `h_level_off`.                                                                        */
-int mcb_run_persistent(const uint32_t *d_records, const int32_t *d_level_off,
-                       const int32_t *h_level_off, int n_levels, const mcb_state *st,
-                       int64_t steps, void *stream);
+/* K1g - mcb_eval_levels on the GROUPED stream: per level the records are sorted by base opcode
+ * and every opcode group is padded to a multiple of 4 records (padding reads and writes a
+ * trash slot), so a thread decodes one opcode per batch and the batch body is branch-free.   */
+int mcb_eval_levels_grouped(const uint32_t *d_records, const int32_t *h_level_off,
+                            int level_begin, int level_end, const mcb_state *st, void *stream);
+
+/* K1pp - every lane tile of `st` (all `st->n_words` columns, `tile_words` at a time) through
+ * every level in ONE cooperative launch, `in_flight` (1..4) tiles at a time with split-phase
+ * grid barriers, on the grouped stream with operand streaming hints (bit 31 of in0 / in1 =
+ * "producer is two or more levels back: stream it through L2"; slots are the low 31 bits).  `st->d_scratch` is the
+ * scratch plane of in-flight slot 0, the others follow at `scratch_plane_words`; `d_sync`
+ * is 64 bytes of caller-owned device memory (zeroed by the call).                           */
+int mcb_run_pipelined(const uint32_t *d_records, const int32_t *d_level_off,
+                      const int32_t *h_level_off, int n_levels, const mcb_state *st,
+                      int64_t tile_words, int in_flight, int64_t scratch_plane_words,
+                      uint32_t *d_sync, int64_t steps, void *stream);
 
 /* K4 - signatures and toggle counts (new capability; no reference counterpart - the
  * reference only peeks one pin at a time, core/simulator.py:285-287).  For each of `n`

@@ -921,6 +921,27 @@ def schedule_batches(records: np.ndarray, level_off: np.ndarray, trash_slot: int
     return out, total // batch
 
 
+def group_levels(records: np.ndarray, level_off: np.ndarray, trash_slot: int, batch: int = 4):
+    """Same grouping as ``schedule_batches`` (per level, per base opcode, padded to a multiple
+    of ``batch`` with trash-slot records) but also returns the level offsets of the grouped
+    stream, for the level kernels that decode the opcode once per batch."""
+    n_levels = len(level_off) - 1
+    out, _ = schedule_batches(records, level_off, trash_slot, batch)
+    base = (records[:, 0] & 0x7F).astype(np.int64)
+    level = np.repeat(np.arange(n_levels, dtype=np.int64), np.diff(level_off).astype(np.int64))
+    live = base != OP_NOP
+    # padded size of every (level, opcode) group, summed per level
+    key = level[live] * 128 + base[live]
+    uniq, counts = np.unique(key, return_counts=True)
+    padded = (counts + batch - 1) // batch * batch
+    per_level = np.zeros(n_levels, dtype=np.int64)
+    np.add.at(per_level, uniq // 128, padded)
+    off = np.zeros(n_levels + 1, dtype=np.int64)
+    np.cumsum(per_level, out=off[1:])
+    assert int(off[-1]) == len(out)
+    return out, off.astype(np.int32)
+
+
 def _sig_name(design: Design, s: int) -> str:
     if s >= design.n_signals:
         return "<temp %d>" % s

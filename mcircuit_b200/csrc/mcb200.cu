@@ -128,6 +128,20 @@ __device__ __forceinline__ uint64_t apply_op(uint32_t op, uint64_t a, uint64_t b
     return (op & MCB_OP_NEG) ? ~r : r;
 }
 
+template <int OP, typename W>
+__device__ __forceinline__ W op_eval(W a, W b, W c) {
+    if (OP == MCB_OP_BUF) return a;
+    if (OP == MCB_OP_AND) return a & b;
+    if (OP == MCB_OP_OR) return a | b;
+    if (OP == MCB_OP_XOR) return a ^ b;
+    if (OP == MCB_OP_ANDN) return a & (W)~b;
+    if (OP == MCB_OP_MUX) return (a & b) | ((W)~a & c);
+    if (OP == MCB_OP_AND3) return a & b & c;
+    if (OP == MCB_OP_OR3) return a | b | c;
+    if (OP == MCB_OP_XOR3) return a ^ b ^ c;
+    return (a & b) | (a & c) | (b & c);                  // MCB_OP_MAJ
+}
+
 template <int CACHE>
 __device__ __forceinline__ ulonglong2 ld_state2(const uint64_t *p) {
     ulonglong2 r;
@@ -227,7 +241,7 @@ static int launch_level(const uint4 *recs, int n, const View &v, cudaStream_t s)
 }
 
 // ------------------------------------------------------------------------------------------
-// K1p: all levels of one lane tile in ONE cooperative launch, a grid barrier between levels.
+// L2-resident small tiles (used by K1pp below): all levels of a lane tile inside one launch.
 // With a small tile (<= 512 words) one level's output rows (5,000 x 4 KB = 20 MB for C5) are
 // still in the 126 MB L2 when the next level reads them as fan-in, and recycled scratch
 // slots are rewritten before their dirty lines are ever evicted, so DRAM traffic drops below
@@ -260,89 +274,167 @@ __device__ __forceinline__ void st_state2_hint(uint64_t *p, ulonglong2 v, uint64
 
 #define SLOT_MASK 0x7fffffffu
 
-template <int U, int HINTS>
-__global__ void __launch_bounds__(1024, 1)
-k_eval_persistent(const uint4 *__restrict__ recs, const int *__restrict__ level_off, int n_levels,
-                  View v, long long n_vec, long long steps) {
-    cg::grid_group grid = cg::this_grid();
-    const uint64_t pol_stream = make_policy_evict_first();
-    const uint64_t pol_keep = make_policy_evict_last();
-    const unsigned nv = (unsigned)n_vec;
-    for (long long step = 0; step < steps; ++step) {
-        for (int lv = 0; lv < n_levels; ++lv) {
-            const int lo = level_off[lv];
-            const int n = level_off[lv + 1] - lo;
-            const int batches = (n + U - 1) / U;
-            // work index = batch * n_vec + column pair (column fastest: a warp stays inside one
-            // batch whenever n_vec is a multiple of 32, so its record loads are broadcasts)
-            const unsigned long long work = (unsigned long long)batches * nv;
-            for (unsigned long long w0 = (unsigned long long)blockIdx.x * blockDim.x; w0 < work;
-                 w0 += (unsigned long long)gridDim.x * blockDim.x) {
-                const unsigned long long w = w0 + threadIdx.x;
-                if (w >= work) continue;
-                const unsigned b = (unsigned)(w / nv);
-                const long long off = (long long)(w - (unsigned long long)b * nv) * 2;
-                const int g0 = lo + (int)b * U;
-                uint4 r[U];
-                ulonglong2 x[U], y[U], z[U];
+// ------------------------------------------------------------------------------------------
+// K1g / K1pp: level kernels on the GROUPED record stream (per level, records sorted by base
+// opcode and every opcode group padded to a multiple of 4 with records on the trash slot), so
+// a thread decodes ONE opcode for its whole batch and the batch body is branch-free.
+//
+// K1pp ("pipelined persistent"): one cooperative launch walks ALL lane tiles, G tiles in flight.
+// Every (tile slot g, level) phase ends with a split-phase grid barrier - arrive now, wait just
+// before the same slot's next level - so while slot g's barrier settles the CTA is already
+// streaming slot g+1's level: no drain, no launch gap, and tiles small enough (256-512 lane
+// words) that a level's rows are still in L2 when the next level reads them.
+// ------------------------------------------------------------------------------------------
+template <int OP, int U, int HINTS>
+__device__ __forceinline__ void level_batch_op(const uint4 (&r)[U], const View &v, long long off,
+                                               uint64_t pol_stream, uint64_t pol_keep) {
+    constexpr int ARITY = (OP == MCB_OP_BUF) ? 1 : (OP >= MCB_OP_MUX ? 3 : 2);
+    ulonglong2 x[U], y[U], z[U];
 #pragma unroll
-                for (int u = 0; u < U; ++u)
-                    r[u] = (g0 + u < lo + n) ? __ldg(recs + g0 + u) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t op = r[u].x & 0x7f;
-                    x[u] = y[u] = z[u] = make_ulonglong2(0, 0);
-                    if (op != MCB_OP_NOP) {
-                        if (HINTS) {
-                            x[u] = ld_state2_hint(row(v, r[u].y & SLOT_MASK) + off,
-                                                  (r[u].y >> 31) ? pol_stream : pol_keep);
-                            if (op != MCB_OP_BUF)
-                                y[u] = ld_state2_hint(row(v, r[u].z & SLOT_MASK) + off,
-                                                      (r[u].z >> 31) ? pol_stream : pol_keep);
-                        } else {
-                            x[u] = ld_state2<1>(row(v, r[u].y & SLOT_MASK) + off);
-                            if (op != MCB_OP_BUF) y[u] = ld_state2<1>(row(v, r[u].z & SLOT_MASK) + off);
-                        }
-                        if (op >= MCB_OP_MUX) z[u] = ld_state2<1>(row(v, r[u].x >> 8) + off);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const uint32_t op = r[u].x & 0xff;
-                    if ((op & 0x7f) != MCB_OP_NOP) {
-                        ulonglong2 o;
-                        o.x = apply_op(op, x[u].x, y[u].x, z[u].x);
-                        o.y = apply_op(op, x[u].y, y[u].y, z[u].y);
-                        if (HINTS) st_state2_hint(row(v, r[u].w & SLOT_MASK) + off, o, pol_keep);
-                        else st_state2(row(v, r[u].w & SLOT_MASK) + off, o);
-                    }
-                }
-            }
-            grid.sync();
+    for (int u = 0; u < U; ++u) {
+        y[u] = z[u] = make_ulonglong2(0, 0);
+        if (HINTS) {
+            x[u] = ld_state2_hint(row(v, r[u].y & SLOT_MASK) + off, (r[u].y >> 31) ? pol_stream : pol_keep);
+            if (ARITY >= 2)
+                y[u] = ld_state2_hint(row(v, r[u].z & SLOT_MASK) + off, (r[u].z >> 31) ? pol_stream : pol_keep);
+        } else {
+            x[u] = ld_state2<1>(row(v, r[u].y & SLOT_MASK) + off);
+            if (ARITY >= 2) y[u] = ld_state2<1>(row(v, r[u].z & SLOT_MASK) + off);
         }
+        if (ARITY >= 3) z[u] = ld_state2<1>(row(v, r[u].x >> 8) + off);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const uint64_t neg = 0ull - (uint64_t)((r[u].x >> 7) & 1u);
+        ulonglong2 o;
+        o.x = op_eval<OP, uint64_t>(x[u].x, y[u].x, z[u].x) ^ neg;
+        o.y = op_eval<OP, uint64_t>(x[u].y, y[u].y, z[u].y) ^ neg;
+        if (HINTS) st_state2_hint(row(v, r[u].w & SLOT_MASK) + off, o, pol_keep);
+        else st_state2(row(v, r[u].w & SLOT_MASK) + off, o);
     }
 }
 
 template <int U, int HINTS>
-static int launch_persistent_t(const uint4 *recs, const int *d_level_off, int n_levels, View v,
-                               long long steps, int max_level, cudaStream_t s) {
-    long long n_vec = (v.n_words + 1) / 2;
+__device__ __forceinline__ void level_batch(const uint4 *__restrict__ recs, const View &v, long long off,
+                                            uint64_t pol_stream, uint64_t pol_keep) {
+    uint4 r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = __ldg(recs + u);
+    switch (r[0].x & 0x7f) {
+        case MCB_OP_BUF:  level_batch_op<MCB_OP_BUF, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_AND:  level_batch_op<MCB_OP_AND, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_OR:   level_batch_op<MCB_OP_OR, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_XOR:  level_batch_op<MCB_OP_XOR, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_ANDN: level_batch_op<MCB_OP_ANDN, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_MUX:  level_batch_op<MCB_OP_MUX, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_AND3: level_batch_op<MCB_OP_AND3, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_OR3:  level_batch_op<MCB_OP_OR3, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_XOR3: level_batch_op<MCB_OP_XOR3, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        case MCB_OP_MAJ:  level_batch_op<MCB_OP_MAJ, U, HINTS>(r, v, off, pol_stream, pol_keep); break;
+        default: break;
+    }
+}
+
+// K1g: one level, grouped stream; same thread mapping as k_eval_level
+template <int U>
+__global__ void __launch_bounds__(256)
+k_eval_level_g(const uint4 *__restrict__ recs, int n_recs, View v, long long n_vec) {
+    const long long col = ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (col >= n_vec) return;
+    for (int g0 = blockIdx.y * U; g0 < n_recs; g0 += gridDim.y * U)
+        level_batch<U, 0>(recs + g0, v, col * 2, 0, 0);
+}
+
+struct PipeArgs {
+    uint64_t *persist;          // column 0 of tile 0
+    long long pstride;
+    uint64_t *scratch;          // plane of in-flight slot 0
+    long long sstride;          // words between scratch rows
+    long long splane;           // words between the scratch planes of in-flight slots
+    uint32_t n_persist;
+    long long n_words;          // all columns
+    int tile_words;
+    int n_tiles;
+    int n_levels;
+    long long steps;
+    unsigned int *sync;         // G monotonic arrival counters, zeroed by the host
+};
+
+template <int U, int G, int HINTS>
+__global__ void __launch_bounds__(1024, 1)
+k_eval_pipelined(const uint4 *__restrict__ recs, const int *__restrict__ level_off, PipeArgs a) {
+    const uint64_t pol_stream = make_policy_evict_first();
+    const uint64_t pol_keep = make_policy_evict_last();
+    unsigned int arrivals[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) arrivals[g] = 0;
+    const unsigned int n_cta = gridDim.x;
+    for (int t0 = 0; t0 < a.n_tiles; t0 += G) {
+        for (long long step = 0; step < a.steps; ++step) {
+            for (int lv = 0; lv < a.n_levels; ++lv) {
+                const int lo = level_off[lv];
+                const int batches = (level_off[lv + 1] - lo) / U;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const int tile = t0 + g;
+                    if (tile >= a.n_tiles) continue;
+                    const long long c0 = (long long)tile * a.tile_words;
+                    long long ncols = a.n_words - c0;
+                    if (ncols > a.tile_words) ncols = a.tile_words;
+                    const unsigned nv = (unsigned)((ncols + 1) / 2);
+                    View v;
+                    v.persist = a.persist + c0;
+                    v.pstride = a.pstride;
+                    v.sstride = a.sstride;
+                    v.scratch_biased = a.scratch + (long long)g * a.splane - (long long)a.n_persist * a.sstride;
+                    v.n_persist = a.n_persist;
+                    v.n_words = ncols;
+                    // wait: every CTA has finished this slot's previous phase
+                    if (threadIdx.x == 0) {
+                        const unsigned int target = arrivals[g] * n_cta;
+                        volatile unsigned int *c = a.sync + g;
+                        while (*c < target) { }
+                        __threadfence();
+                    }
+                    __syncthreads();
+                    // my contiguous share of the phase's (batch, column pair) items
+                    const unsigned long long work = (unsigned long long)batches * nv;
+                    const unsigned long long w_lo = work * blockIdx.x / n_cta;
+                    const unsigned long long w_hi = work * (blockIdx.x + 1) / n_cta;
+                    for (unsigned long long w = w_lo + threadIdx.x; w < w_hi; w += blockDim.x) {
+                        const unsigned b = (unsigned)(w / nv);
+                        const long long off = (long long)(w - (unsigned long long)b * nv) * 2;
+                        level_batch<U, HINTS>(recs + lo + (int)b * U, v, off, pol_stream, pol_keep);
+                    }
+                    // arrive: publish this CTA's rows of the phase
+                    __syncthreads();
+                    if (threadIdx.x == 0) {
+                        __threadfence();
+                        atomicAdd(a.sync + g, 1u);
+                    }
+                    arrivals[g] += 1;
+                }
+            }
+        }
+    }
+}
+
+template <int U, int G>
+static int launch_pipelined_ug(const uint4 *recs, const int *d_level_off, PipeArgs a, cudaStream_t s) {
     int block = g_tune.persist_block;
     if (block > 1024) block = 1024;
     if (block < 32) block = 32;
     block = block / 32 * 32;
+    const int H = g_tune.persist_hints ? 1 : 0;
+    const void *fn = H ? (const void *)k_eval_pipelined<U, G, 1> : (const void *)k_eval_pipelined<U, G, 0>;
     int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_eval_persistent<U, HINTS>, block, 0));
-    if (per_sm < 1) return fail(MCB_ERR_CUDA, "persistent kernel does not fit on an SM");
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, block, 0));
+    if (per_sm < 1) return fail(MCB_ERR_CUDA, "pipelined kernel does not fit on an SM");
     if (g_tune.persist_ctas_per_sm > 0 && per_sm > g_tune.persist_ctas_per_sm) per_sm = g_tune.persist_ctas_per_sm;
-    const long long work = (long long)((max_level + U - 1) / U) * n_vec;
-    long long grid = (long long)sm_count() * per_sm;     // few, fat CTAs: the grid barrier is
-    if (grid > (work + block - 1) / block) grid = (work + block - 1) / block;   // one atomic per CTA
-    if (grid < 1) grid = 1;
-    void *args[] = {(void *)&recs, (void *)&d_level_off, (void *)&n_levels, (void *)&v, (void *)&n_vec,
-                    (void *)&steps};
-    CUDA_TRY(cudaLaunchCooperativeKernel((void *)k_eval_persistent<U, HINTS>, dim3((unsigned)grid),
-                                         dim3(block), args, 0, s));
+    const long long grid = (long long)sm_count() * per_sm;
+    CUDA_TRY(cudaMemsetAsync(a.sync, 0, 64, s));
+    void *args[] = {(void *)&recs, (void *)&d_level_off, (void *)&a};
+    CUDA_TRY(cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(block), args, 0, s));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return 0;
 }
@@ -455,20 +547,6 @@ __device__ __forceinline__ W apply_op_w(uint32_t op, W a, W b, W c) {
 // slot).  The opcode is decoded once per batch; inside, the U load / compute / store chains
 // are straight-line and branch-free, so the compiler interleaves them and a single warp keeps
 // U x 2..3 loads in flight.  Every load of a batch is issued before its first store.
-template <int OP, typename W>
-__device__ __forceinline__ W op_eval(W a, W b, W c) {
-    if (OP == MCB_OP_BUF) return a;
-    if (OP == MCB_OP_AND) return a & b;
-    if (OP == MCB_OP_OR) return a | b;
-    if (OP == MCB_OP_XOR) return a ^ b;
-    if (OP == MCB_OP_ANDN) return a & (W)~b;
-    if (OP == MCB_OP_MUX) return (a & b) | ((W)~a & c);
-    if (OP == MCB_OP_AND3) return a & b & c;
-    if (OP == MCB_OP_OR3) return a | b | c;
-    if (OP == MCB_OP_XOR3) return a ^ b ^ c;
-    return (a & b) | (a & c) | (b & c);                  // MCB_OP_MAJ
-}
-
 template <int OP, typename W, int U, class Cols>
 __device__ __forceinline__ void run_batch_op(const uint4 *r4, const Cols &cols) {
     constexpr int ARITY = (OP == MCB_OP_BUF) ? 1 : (OP >= MCB_OP_MUX ? 3 : 2);
@@ -955,30 +1033,81 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
     return 0;
 }
 
-int mcb_run_persistent(const uint32_t *d_records, const int32_t *d_level_off,
-                       const int32_t *h_level_off, int n_levels, const mcb_state *st, int64_t steps,
-                       void *stream) {
+int mcb_run_pipelined(const uint32_t *d_records, const int32_t *d_level_off,
+                      const int32_t *h_level_off, int n_levels, const mcb_state *st,
+                      int64_t tile_words, int in_flight, int64_t scratch_plane_words,
+                      uint32_t *d_sync, int64_t steps, void *stream) {
+    if (!st) return fail(MCB_ERR_ARG, "state is NULL");
+    mcb_state one = *st;                     // geometry of one tile for the stride checks
+    if (one.n_words > tile_words) one.n_words = tile_words;
+    int rc = check_state(&one);
+    if (rc) return rc;
+    if (st->n_persist > 0 && st->persist_stride < ((st->n_words + 1) & ~1ll))
+        return fail(MCB_ERR_ARG, "persist_stride smaller than the lane extent");
+    if (!d_records || !d_level_off || !h_level_off || !d_sync || n_levels < 0 || steps < 0 ||
+        tile_words < 2 || (tile_words & 1) || in_flight < 1 || in_flight > 4)
+        return fail(MCB_ERR_ARG, "bad pipelined-run arguments");
+    if (steps == 0 || n_levels == 0 || st->n_words == 0) return 0;
+    const int U = g_tune.persist_unroll >= 4 ? 4 : (g_tune.persist_unroll >= 2 ? 2 : 1);
+    for (int l = 0; l <= n_levels; ++l)
+        if (h_level_off[l] % 4) return fail(MCB_ERR_ARG, "grouped stream: levels must be multiples of 4");
+    PipeArgs a;
+    a.persist = st->d_persist;
+    a.pstride = st->persist_stride;
+    a.scratch = st->d_scratch;
+    a.sstride = st->scratch_stride;
+    a.splane = scratch_plane_words;
+    a.n_persist = (uint32_t)st->n_persist;
+    a.n_words = st->n_words;
+    a.tile_words = (int)tile_words;
+    a.n_tiles = (int)((st->n_words + tile_words - 1) / tile_words);
+    a.n_levels = n_levels;
+    a.steps = steps;
+    a.sync = d_sync;
+    if (a.n_tiles > 1 && (st->n_slots > st->n_persist) && scratch_plane_words <= 0)
+        return fail(MCB_ERR_ARG, "scratch_plane_words must be given when several tiles are in flight");
+    const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
+    cudaStream_t s = (cudaStream_t)stream;
+#define MCB_PP(UU)                                                                         \
+    switch (in_flight) {                                                                   \
+        case 1: return launch_pipelined_ug<UU, 1>(recs, d_level_off, a, s);                 \
+        case 2: return launch_pipelined_ug<UU, 2>(recs, d_level_off, a, s);                 \
+        case 3: return launch_pipelined_ug<UU, 3>(recs, d_level_off, a, s);                 \
+        default: return launch_pipelined_ug<UU, 4>(recs, d_level_off, a, s);                \
+    }
+    if (U >= 2) { MCB_PP(2) }
+    MCB_PP(1)
+#undef MCB_PP
+}
+
+int mcb_eval_levels_grouped(const uint32_t *d_records, const int32_t *h_level_off, int level_begin,
+                            int level_end, const mcb_state *st, void *stream) {
     int rc = check_state(st);
     if (rc) return rc;
-    if (!d_records || !d_level_off || !h_level_off || n_levels < 0 || steps < 0)
-        return fail(MCB_ERR_ARG, "bad persistent-run arguments");
-    if (steps == 0 || n_levels == 0 || st->n_words == 0) return 0;
-    int max_level = 0;
-    for (int l = 0; l < n_levels; ++l) {
-        const int n = h_level_off[l + 1] - h_level_off[l];
-        if (n > max_level) max_level = n;
-    }
+    if (!d_records || !h_level_off || level_begin < 0 || level_end < level_begin)
+        return fail(MCB_ERR_ARG, "bad netlist arguments");
     const View v = make_view(st);
     const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
-    const int H = g_tune.persist_hints ? 1 : 0;
-    cudaStream_t s = (cudaStream_t)stream;
-#define MCB_LP(UU)                                                                         \
-    (H ? launch_persistent_t<UU, 1>(recs, d_level_off, n_levels, v, steps, max_level, s)    \
-       : launch_persistent_t<UU, 0>(recs, d_level_off, n_levels, v, steps, max_level, s))
-    if (g_tune.persist_unroll >= 4) return MCB_LP(4);
-    if (g_tune.persist_unroll >= 2) return MCB_LP(2);
-    return MCB_LP(1);
-#undef MCB_LP
+    const long long n_vec = (v.n_words + 1) / 2;
+    int block = g_tune.level_block;
+    if (block > 256) block = 256;
+    if (block < 32) block = 32;
+    while (block > 32 && block / 2 >= n_vec) block /= 2;
+    const long long gx = (n_vec + block - 1) / block;
+    const int U = g_tune.level_unroll >= 4 ? 4 : (g_tune.level_unroll >= 2 ? 2 : 1);
+    for (int l = level_begin; l < level_end; ++l) {
+        const int lo = h_level_off[l], n = h_level_off[l + 1] - lo;
+        if (n <= 0) continue;
+        if ((lo | n) % 4) return fail(MCB_ERR_ARG, "grouped stream: levels must be multiples of 4");
+        long long gy = n / U;
+        if (gy > 65535) gy = 65535;
+        dim3 grid((unsigned)gx, (unsigned)gy, 1);
+        if (U == 4) k_eval_level_g<4><<<grid, block, 0, (cudaStream_t)stream>>>(recs + lo, n, v, n_vec);
+        else if (U == 2) k_eval_level_g<2><<<grid, block, 0, (cudaStream_t)stream>>>(recs + lo, n, v, n_vec);
+        else k_eval_level_g<1><<<grid, block, 0, (cudaStream_t)stream>>>(recs + lo, n, v, n_vec);
+        LAUNCH_CHECK("k_eval_level_g");
+    }
+    return 0;
 }
 
 int mcb_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,

@@ -72,7 +72,7 @@ class B200Engine(Executor):
                  keep="auto", observe: Sequence[str] = (), tile_words: Optional[int] = None,
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
-                 resident_word_bytes=0):
+                 resident_word_bytes=0, in_flight=2):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -107,9 +107,11 @@ class B200Engine(Executor):
         if mode == "auto":
             # per-level launches pay off only when one level keeps the whole GPU busy
             mode = "levels" if avg_level * min(self.words, DEFAULT_TILE_WORDS) >= (1 << 19) else "resident"
-        if mode not in ("levels", "resident", "persistent"):
-            raise ValueError("mode must be 'auto', 'levels', 'resident' or 'persistent'")
+        if mode not in ("levels", "levels_grouped", "resident", "persistent"):
+            raise ValueError("mode must be 'auto', 'levels', 'levels_grouped', 'resident' or 'persistent'")
         self.mode = mode
+
+        self.in_flight = max(1, min(4, int(in_flight)))     # tiles in flight of the pipelined kernel
 
         # ---- tiling ------------------------------------------------------------------------------
         persist_bytes = P * self.stride * 8
@@ -138,7 +140,8 @@ class B200Engine(Executor):
         else:
             self._plane = self.rt.zeros_words(P * self.stride + _ALIGN_WORDS)
             self.scratch_stride = _round_up(tile_words, _ALIGN_WORDS)
-            self._scratch = self.rt.zeros_words(S * self.scratch_stride + _ALIGN_WORDS)
+            planes = self.in_flight if mode == "persistent" else 1
+            self._scratch = self.rt.zeros_words(planes * S * self.scratch_stride + _ALIGN_WORDS)
         self._d_records = self.rt.to_device(program.records)
         self._h_level_off = np.ascontiguousarray(program.level_off, dtype=np.int32)
         self._resident = None      # (d_records in batches, h_level_off), built on first use
@@ -203,18 +206,44 @@ class B200Engine(Executor):
         self.steps_done += steps
 
     def _run_raw(self, steps):
+        if self.mode == "persistent":
+            self._run_pipelined(steps)
+            return
         for c0, n in self._tiles():
             self._run_tile(c0, n, steps)
 
+    def _grouped(self):
+        """Grouped (per level, per opcode, padded to 4) hinted record stream on the device."""
+        if getattr(self, "_grouped_stream", None) is None:
+            rec, off = compiler.group_levels(self.program.records_hinted, self.program.level_off,
+                                             self.trash_slot, 4)
+            self._grouped_stream = (self.rt.to_device(rec), self.rt.to_device(off), off)
+        return self._grouped_stream
+
+    def _run_pipelined(self, steps):
+        """K1pp: every tile through every level in one cooperative launch, ``in_flight`` tiles
+        at a time (split-phase grid barriers)."""
+        d_rec, d_off, h_off = self._grouped()
+        if getattr(self, "_sync", None) is None:
+            self._sync = self.rt.zeros_words(8)
+        P, S = self.program.n_persist, self.program.n_scratch + 1
+        if self.n_tiles == 1:
+            st = self._state_for(0, self.words)
+            self.rt.run_pipelined(d_rec, d_off, h_off, self.program.n_levels, st, _round_up(self.words, 2), 1,
+                                  0, self._sync, steps)
+        else:
+            st = self.rt.make_state(self._plane, self.stride, self._scratch, self.scratch_stride, P, P + S,
+                                    self.words)
+            self.rt.run_pipelined(d_rec, d_off, h_off, self.program.n_levels, st, self.tile_words,
+                                  self.in_flight, S * self.scratch_stride, self._sync, steps)
+
     def _run_tile(self, c0, n, steps):
         """All ``steps`` passes of one lane tile (tiles are independent: lanes never interact)."""
-        if self.mode == "persistent":
-            if getattr(self, "_persistent", None) is None:
-                self._persistent = (self.rt.to_device(self.program.records_hinted),
-                                    self.rt.to_device(self._h_level_off))
-            d_rec, d_off = self._persistent
-            self.rt.run_persistent(d_rec, d_off, self._h_level_off, self.program.n_levels,
-                                   self._state_for(c0, n), steps)
+        if self.mode == "levels_grouped":
+            d_rec, _, h_off = self._grouped()
+            st = self._state_for(c0, n)
+            for _ in range(int(steps)):
+                self.rt.eval_levels_grouped(d_rec, h_off, 0, self.program.n_levels, st)
         elif self.mode == "resident":
             if self._resident is None:
                 rec, n_batches = compiler.schedule_batches(self.program.records, self.program.level_off,

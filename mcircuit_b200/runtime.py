@@ -46,8 +46,9 @@ _PROTOTYPES = [
     ("mcb_eval_levels", c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(McbState), c_void_p]),
     ("mcb_latch", c_int, [c_void_p, c_int, POINTER(McbState), c_void_p]),
     ("mcb_run", c_int, [c_void_p, c_void_p, c_int, POINTER(McbState), c_int64, c_int, c_void_p]),
-    ("mcb_run_persistent", c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(McbState), c_int64,
-                                   c_void_p]),
+    ("mcb_eval_levels_grouped", c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(McbState), c_void_p]),
+    ("mcb_run_pipelined", c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(McbState), c_int64, c_int,
+                                  c_int64, c_void_p, c_int64, c_void_p]),
     ("mcb_signature", c_int, [c_void_p, c_int, POINTER(McbState), c_int64, c_void_p, c_void_p,
                               c_void_p]),
     ("mcb_toggle_accum", c_int, [c_void_p, c_int, POINTER(McbState), c_void_p, c_int64, c_void_p,
@@ -179,11 +180,19 @@ class CudaRuntime:
                 d_records.data_ptr(), h_level_off.ctypes.data, int(n_levels), ctypes.byref(st),
                 int(steps), int(mode), self._stream()))
 
-    def run_persistent(self, d_records, d_level_off, h_level_off: np.ndarray, n_levels, st: McbState, steps):
+    def eval_levels_grouped(self, d_records, h_level_off: np.ndarray, lo, hi, st: McbState):
         with self.torch.cuda.device(self.device):
-            self._check(self.lib.mcb_run_persistent(
+            self._check(self.lib.mcb_eval_levels_grouped(
+                d_records.data_ptr(), h_level_off.ctypes.data, int(lo), int(hi), ctypes.byref(st),
+                self._stream()))
+
+    def run_pipelined(self, d_records, d_level_off, h_level_off: np.ndarray, n_levels, st: McbState,
+                      tile_words, in_flight, scratch_plane_words, d_sync, steps):
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.mcb_run_pipelined(
                 d_records.data_ptr(), d_level_off.data_ptr(), h_level_off.ctypes.data, int(n_levels),
-                ctypes.byref(st), int(steps), self._stream()))
+                ctypes.byref(st), int(tile_words), int(in_flight), int(scratch_plane_words),
+                d_sync.data_ptr(), int(steps), self._stream()))
 
     def signature(self, d_slots, n, st: McbState, col_offset, d_popcount, d_checksum):
         with self.torch.cuda.device(self.device):

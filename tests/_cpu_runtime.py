@@ -158,13 +158,32 @@ class CpuRuntime:
             for _ in range(int(steps)):
                 self.eval_levels(d_records, h_level_off, 0, n_levels, st)
 
-    def run_persistent(self, d_records, d_level_off, h_level_off, n_levels, st, steps):
+    def eval_levels_grouped(self, d_records, h_level_off, lo, hi, st):
+        recs = d_records.astype(np.int64)
+        recs[:, 1] &= 0x7FFFFFFF
+        recs[:, 2] &= 0x7FFFFFFF
+        self.eval_levels(recs, h_level_off, lo, hi, st)
+
+    def run_pipelined(self, d_records, d_level_off, h_level_off, n_levels, st, tile_words, in_flight,
+                      scratch_plane_words, d_sync, steps):
         recs = d_records.astype(np.int64)
         recs[:, 1] &= 0x7FFFFFFF          # strip the streaming hints
         recs[:, 2] &= 0x7FFFFFFF
         assert np.array_equal(np.asarray(d_level_off), np.asarray(h_level_off))
-        for _ in range(int(steps)):
-            self.eval_levels(recs, h_level_off, 0, n_levels, st)
+        assert all(int(x) % 4 == 0 for x in h_level_off)
+        n_tiles = (st.n_words + tile_words - 1) // tile_words
+        for t0 in range(0, n_tiles, in_flight):
+            for _ in range(int(steps)):
+                for lv in range(n_levels):                      # tiles of a group advance level by level
+                    for g in range(in_flight):
+                        tile = t0 + g
+                        if tile >= n_tiles:
+                            continue
+                        c0 = tile * tile_words
+                        sub = _State(st.persist, st.pstride, st.pcol + c0, st.scratch, st.sstride,
+                                     st.scol + g * scratch_plane_words, st.n_persist, st.n_slots,
+                                     min(tile_words, st.n_words - c0))
+                        self.eval_levels(recs, h_level_off, lv, lv + 1, sub)
 
     # ---- K4 / K5 ---------------------------------------------------------------------------------
     def signature(self, d_slots, n, st, col_offset, d_popcount, d_checksum):

@@ -31,7 +31,8 @@ def test_native_library_is_the_one_running(cuda_rt):
 @pytest.mark.parametrize("case", TRACES, ids=[c["name"] for c in TRACES])
 @pytest.mark.parametrize("mode,keep,map_pins", [("resident", "all", True), ("levels", "ports", True),
                                                 ("levels", "all", False), ("resident", "ports", False),
-                                                ("persistent", "ports", True), ("persistent", "all", False)])
+                                                ("persistent", "ports", True), ("persistent", "all", False),
+                                                ("levels_grouped", "ports", True)])
 def test_gpu_traces(case, mode, keep, map_pins):
     run_trace_case(case, gpu_factory(mode, keep, map_pins), skip_unobservable=(keep == "ports"))
 
@@ -242,15 +243,19 @@ def test_gpu_persistent_level_kernel_variants(cuda_rt, unroll, hints):
         cuda_rt.set_tuning("persist_hints", hints)
         root = circuits.random_dag(MD, n_gates=20_000, depth=40, n_inputs=256, seed=77)
         lanes = 64 * 320
-        a = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="levels")
-        b = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="persistent", tile_words=64)
-        assert b.n_tiles == 5
-        for e in (a, b):
+        pa = ca = None
+        for mode, kw in (("levels", {}), ("levels_grouped", {"tile_words": 64}),
+                         ("persistent", {"tile_words": 64, "in_flight": 1}),
+                         ("persistent", {"tile_words": 64, "in_flight": 2}),
+                         ("persistent", {"tile_words": 64, "in_flight": 3}),
+                         ("persistent", {"tile_words": 32, "in_flight": 4})):
+            e = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode=mode, **kw)
             e.randomize_inputs()
             e.run(1)
-        pa, ca = a.signature()
-        pb, cb = b.signature()
-        assert np.array_equal(pa, pb) and np.array_equal(ca, cb)
+            p_, c_ = e.signature()
+            if pa is None:
+                pa, ca = p_, c_
+            assert np.array_equal(pa, p_) and np.array_equal(ca, c_), (mode, kw)
         # sequential circuit, several steps inside one cooperative launch
         c = B200Engine(circuits.counter_circuit(MD), 1, True, lanes=128, mode="persistent")
         c.run(7)
