@@ -102,15 +102,6 @@ class B200Engine(Executor):
         if self.trash_slot >= compiler.IN2_LIMIT:
             raise compiler.CircuitError("too many slots for the resident kernel's padding records")
 
-        # ---- execution mode -------------------------------------------------------------------
-        avg_level = program.n_ops / max(1, program.n_levels)
-        if mode == "auto":
-            # per-level launches pay off only when one level keeps the whole GPU busy
-            mode = "levels" if avg_level * min(self.words, DEFAULT_TILE_WORDS) >= (1 << 19) else "resident"
-        if mode not in ("levels", "levels_grouped", "resident", "persistent"):
-            raise ValueError("mode must be 'auto', 'levels', 'levels_grouped', 'resident' or 'persistent'")
-        self.mode = mode
-
         self.in_flight = max(1, min(4, int(in_flight)))     # tiles in flight of the pipelined kernel
 
         # ---- tiling ------------------------------------------------------------------------------
@@ -130,6 +121,16 @@ class B200Engine(Executor):
             raise MemoryError(
                 "state does not fit: %d persistent slots x %d words + %d scratch slots x %d words"
                 % (P, self.stride, S, tile_words))
+
+        # ---- execution mode -------------------------------------------------------------------
+        avg_level = program.n_ops / max(1, program.n_levels)
+        if mode == "auto":
+            # per-level launches pay off only when one level of one tile keeps the whole GPU
+            # busy for longer than a launch gap; otherwise one resident launch walks everything
+            mode = "levels" if avg_level * self.tile_words >= (1 << 19) else "resident"
+        if mode not in ("levels", "levels_grouped", "resident", "persistent"):
+            raise ValueError("mode must be 'auto', 'levels', 'levels_grouped', 'resident' or 'persistent'")
+        self.mode = mode
 
         # ---- buffers (torch owns them) ---------------------------------------------------------------
         if self.n_tiles == 1:
