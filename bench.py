@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU baseline duration")
+    ap.add_argument("--streams", type=int, default=0, help="compute streams that independent tiles alternate over (0 = engine default)")
     ap.add_argument("--tune", default="", help="comma list key=value for mcb_set_tuning")
     ap.add_argument("--verify", action="store_true", help="check sampled columns against the oracle")
     return ap.parse_args()
@@ -178,6 +179,29 @@ def run_reference(a):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's threads (and therefore its pinned host buffers, first touch) to the
+    NUMA node its GPU hangs off, so host<->device copies do not cross the socket link."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bus = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bus).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -194,6 +218,7 @@ def run_ours(a):
     else:
         torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
 
     import __graft_entry__ as ge
     if rank == 0:
@@ -207,7 +232,7 @@ def run_ours(a):
     root = circuits.random_dag(n_gates=a.gates, depth=a.depth, n_inputs=a.inputs)
     words = a.lanes_per_gpu // 64
     eng = B200Engine(root, 1, True, lanes=a.lanes_per_gpu, device=local, keep="ports", mode=a.mode,
-                     tile_words=(a.tile_words or None), lane_word_offset=rank * words)
+                     tile_words=(a.tile_words or None), lane_word_offset=rank * words, streams=(a.streams or None))
     t_build = time.time() - t_build
     for kv in filter(None, a.tune.split(",")):
         k, v = kv.split("=")
@@ -367,11 +392,11 @@ def run_ours(a):
                        "inputs": a.inputs, "lanes_per_gpu": a.lanes_per_gpu, "lanes_total": total_lanes,
                        "levels": prog.n_levels, "tile_words": eng.tile_words, "tiles": eng.n_tiles,
                        "persistent_slots": prog.n_persist, "scratch_slots": prog.n_scratch,
-                       "mode": eng.mode, "parallelism": "lanes sharded x%d, netlist replicated" % world,
+                       "mode": eng.mode, "streams": eng.n_streams, "parallelism": "lanes sharded x%d, netlist replicated" % world,
                        "l2": "inputs larger than L2: %.1f GB of state streamed per step"
                              % (alg_bytes_step / 1e9),
                        "stimulus": "splitmix64 counter-based, generated on device",
-                       "compile_s": round(t_build, 1), "tuning": a.tune},
+                       "compile_s": round(t_build, 1), "tuning": a.tune, "numa_node": numa},
             "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "signature_popcount_sum": int(signature_host[:sig["n"]].sum()),
         }

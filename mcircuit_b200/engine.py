@@ -27,7 +27,8 @@ from .runtime import MODE_LEVELS, MODE_RESIDENT, RESIDENT_UNROLL
 SEED = 0x6D63697263756974      # "mcircuit"
 _ALL = 0xFFFFFFFFFFFFFFFF
 _ALIGN_WORDS = 16              # rows start on 128-byte boundaries
-DEFAULT_TILE_WORDS = 2048      # 16 KB rows: best measured trade of launch count against footprint
+DEFAULT_TILE_WORDS = 1280      # 10 KB rows x 3 streams: best measured (profiles/r01_sweep_streams.jsonl)
+DEFAULT_STREAMS = 3
 
 
 def _round_up(x, m):
@@ -72,7 +73,7 @@ class B200Engine(Executor):
                  keep="auto", observe: Sequence[str] = (), tile_words: Optional[int] = None,
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
-                 resident_word_bytes=0, in_flight=2):
+                 resident_word_bytes=0, in_flight=2, streams=None):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -103,27 +104,40 @@ class B200Engine(Executor):
             raise compiler.CircuitError("too many slots for the resident kernel's padding records")
 
         self.in_flight = max(1, min(4, int(in_flight)))     # tiles in flight of the pipelined kernel
+        # level mode: independent tiles alternate over this many CUDA streams (each with its own
+        # scratch plane) so one tile's launch gaps and kernel tails are filled by another's work
+        if streams is None:
+            streams = DEFAULT_STREAMS
+        self.n_streams = max(1, min(4, int(streams))) if hasattr(self.rt, "torch") else 1
+        self._streams = None
 
         # ---- tiling ------------------------------------------------------------------------------
         persist_bytes = P * self.stride * 8
+        avg_level = program.n_ops / max(1, program.n_levels)
+        wide = (mode in ("levels", "levels_grouped") or
+                (mode == "auto" and avg_level * min(self.words, DEFAULT_TILE_WORDS) >= (1 << 19)))
         if tile_words is None:
-            if (P + S) * self.stride * 8 <= budget:
+            fits = (P + S) * self.stride * 8 <= budget
+            if fits and not (wide and self.n_streams > 1 and self.words > 2 * DEFAULT_TILE_WORDS):
                 tile_words = self.words                      # everything resident, one tile
             else:
+                # wide level sweeps run best as ~10 KB-row tiles alternating over a few streams
                 room = max(budget - persist_bytes, 0)
-                tile_words = max(_ALIGN_WORDS, min(DEFAULT_TILE_WORDS, (room // max(1, S * 8)) // _ALIGN_WORDS * _ALIGN_WORDS))
+                planes = max(self.n_streams, self.in_flight)
+                tile_words = max(_ALIGN_WORDS, min(DEFAULT_TILE_WORDS,
+                                                   (room // max(1, S * 8 * planes)) // _ALIGN_WORDS * _ALIGN_WORDS))
         tile_words = int(min(tile_words, self.words))
         if tile_words < self.words:
             tile_words = max(_ALIGN_WORDS, tile_words // _ALIGN_WORDS * _ALIGN_WORDS)
         self.tile_words = tile_words
         self.n_tiles = (self.words + tile_words - 1) // tile_words
-        if persist_bytes + S * _round_up(tile_words, _ALIGN_WORDS) * 8 > budget:
+        if persist_bytes + S * _round_up(tile_words, _ALIGN_WORDS) * 8 * (max(self.n_streams, self.in_flight)
+                                                                            if tile_words < self.words else 1) > budget:
             raise MemoryError(
                 "state does not fit: %d persistent slots x %d words + %d scratch slots x %d words"
                 % (P, self.stride, S, tile_words))
 
         # ---- execution mode -------------------------------------------------------------------
-        avg_level = program.n_ops / max(1, program.n_levels)
         if mode == "auto":
             # per-level launches pay off only when one level of one tile keeps the whole GPU
             # busy for longer than a launch gap; otherwise one resident launch walks everything
@@ -141,7 +155,7 @@ class B200Engine(Executor):
         else:
             self._plane = self.rt.zeros_words(P * self.stride + _ALIGN_WORDS)
             self.scratch_stride = _round_up(tile_words, _ALIGN_WORDS)
-            planes = self.in_flight if mode == "persistent" else 1
+            planes = self.in_flight if mode == "persistent" else self.n_streams
             self._scratch = self.rt.zeros_words(planes * S * self.scratch_stride + _ALIGN_WORDS)
         self._d_records = self.rt.to_device(program.records)
         self._h_level_off = np.ascontiguousarray(program.level_off, dtype=np.int32)
@@ -161,7 +175,7 @@ class B200Engine(Executor):
     # ------------------------------------------------------------------------------------------
     # state views
     # ------------------------------------------------------------------------------------------
-    def _state_for(self, col0, n_words, whole=False):
+    def _state_for(self, col0, n_words, whole=False, plane=0):
         P, S = self.program.n_persist, self.program.n_scratch + 1
         if self.n_tiles == 1:
             return self.rt.make_state(self._plane, self.stride, self._plane, self.stride, P, P + S,
@@ -171,7 +185,8 @@ class B200Engine(Executor):
             # persistent rows only (pin access, stimulus, signatures)
             return self.rt.make_state(self._plane, self.stride, None, 0, P, P, n_words, col_offset=col0)
         return self.rt.make_state(self._plane, self.stride, self._scratch, self.scratch_stride,
-                                  P, P + S, n_words, col_offset=col0)
+                                  P, P + S, n_words, col_offset=col0,
+                                  scratch_col_offset=plane * S * self.scratch_stride)
 
     def _tiles(self):
         for t in range(self.n_tiles):
@@ -210,8 +225,27 @@ class B200Engine(Executor):
         if self.mode == "persistent":
             self._run_pipelined(steps)
             return
+        if self.n_streams > 1 and self.n_tiles > 1 and self.mode in ("levels", "levels_grouped"):
+            torch = self.rt.torch
+            main = torch.cuda.current_stream(self.rt.device)
+            streams = self._compute_streams()
+            for st in streams:
+                st.wait_stream(main)
+            for t, (c0, n) in enumerate(self._tiles()):
+                k = t % len(streams)
+                with torch.cuda.stream(streams[k]):
+                    self._run_tile(c0, n, steps, plane=k)
+            for st in streams:
+                main.wait_stream(st)
+            return
         for c0, n in self._tiles():
             self._run_tile(c0, n, steps)
+
+    def _compute_streams(self):
+        if self._streams is None:
+            torch = self.rt.torch
+            self._streams = [torch.cuda.Stream(self.rt.device) for _ in range(self.n_streams)]
+        return self._streams
 
     def _grouped(self):
         """Grouped (per level, per opcode, padded to 4) hinted record stream on the device."""
@@ -238,11 +272,11 @@ class B200Engine(Executor):
             self.rt.run_pipelined(d_rec, d_off, h_off, self.program.n_levels, st, self.tile_words,
                                   self.in_flight, S * self.scratch_stride, self._sync, steps)
 
-    def _run_tile(self, c0, n, steps):
+    def _run_tile(self, c0, n, steps, plane=0):
         """All ``steps`` passes of one lane tile (tiles are independent: lanes never interact)."""
         if self.mode == "levels_grouped":
             d_rec, _, h_off = self._grouped()
-            st = self._state_for(c0, n)
+            st = self._state_for(c0, n, plane=plane)
             for _ in range(int(steps)):
                 self.rt.eval_levels_grouped(d_rec, h_off, 0, self.program.n_levels, st)
         elif self.mode == "resident":
@@ -258,7 +292,7 @@ class B200Engine(Executor):
                             MODE_RESIDENT | (self.resident_batch << 8) | (self.resident_word_bytes << 16))
         else:
             self.rt.run(self._d_records, self._h_level_off, self.program.n_levels,
-                        self._state_for(c0, n), steps, MODE_LEVELS)
+                        self._state_for(c0, n, plane=plane), steps, MODE_LEVELS)
 
     def run_host(self, in_plan, h_in, out_plan, h_out, steps: int = 1):
         """Host buffers in, host buffers out, pipelined by lane tile: the stimulus rows of
@@ -287,15 +321,25 @@ class B200Engine(Executor):
             ev = torch.cuda.Event()
             ev.record(s_in)
             ready.append(ev)
-        for (c0, n), ev in zip(tiles, ready):
-            main.wait_event(ev)
-            self._run_tile(c0, n, steps)
+        multi = self.n_streams > 1 and len(tiles) > 1 and self.mode in ("levels", "levels_grouped")
+        comp = self._compute_streams() if multi else [main]
+        if multi:
+            for cs in comp:
+                cs.wait_stream(main)
+        for t, ((c0, n), ev) in enumerate(zip(tiles, ready)):
+            cs = comp[t % len(comp)]
+            cs.wait_event(ev)
+            with torch.cuda.stream(cs):
+                self._run_tile(c0, n, steps, plane=(t % len(comp)) if multi else 0)
             done = torch.cuda.Event()
-            done.record(main)
+            done.record(cs)
             s_out.wait_event(done)
             for first, count, k in out_plan["runs"]:
                 self.rt.copy2d(h_out.data_ptr() + k * out_pitch + c0 * 8, out_pitch,
                                base + (first * self.stride + c0) * 8, pitch, n * 8, count, False, s_out)
+        if multi:
+            for cs in comp:
+                main.wait_stream(cs)
         main.wait_stream(s_out)
         self.steps_done += int(steps)
 

@@ -302,3 +302,28 @@ def test_gpu_capture_waveform_and_program_cache(tmp_path):
     pa, ca = a.signature()
     pb, cb = b.signature()
     assert np.array_equal(pa, pb) and np.array_equal(ca, cb)
+
+
+@pytest.mark.parametrize("streams", [2, 3])
+def test_gpu_tiles_on_several_streams(streams):
+    """Independent lane tiles alternating over several CUDA streams (own scratch plane each)."""
+    import torch
+    root = circuits.random_dag(MD, n_gates=6000, depth=20, n_inputs=64, seed=21)
+    lanes = 64 * 32 * 7
+    a = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="levels", tile_words=32)
+    b = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="levels", tile_words=32, streams=streams)
+    assert b.n_tiles == 7 and b.n_streams == streams
+    for e in (a, b):
+        e.randomize_inputs()
+        e.run(2)
+    pa, ca = a.signature()
+    pb, cb = b.signature()
+    assert np.array_equal(pa, pb) and np.array_equal(ca, cb)
+    in_plan, out_plan = b.io_plan(b.input_pins()), b.io_plan(b.output_pins())
+    h_in = torch.empty((in_plan["n"], b.words), dtype=torch.int64, pin_memory=True)
+    h_out = torch.zeros((out_plan["n"], b.words), dtype=torch.int64, pin_memory=True)
+    h_in.numpy()[:] = restate.stimulus_word(np.arange(64)[:, None], np.arange(b.words)[None, :]).view(np.int64)
+    b.run_host(in_plan, h_in, out_plan, h_out)
+    torch.cuda.synchronize()
+    for k, p in enumerate(b.output_pins()):
+        assert np.array_equal(h_out[k].numpy().view(np.uint64), a.get_pin_planes(p)[0]), p
