@@ -88,7 +88,9 @@ int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void 
  * delimit segments that are multiples of B.
  * Bits 8..15 of `mode` carry B (0 = MCB_RESIDENT_UNROLL; 4 or 8), bits 16..23 the bytes
  * of a lane word one thread owns (0 = automatic; 8, 4, 2 or 1).  mode 1: per-level launches
- * captured once in a CUDA graph and replayed `steps` times.                               */
+ * captured once in a CUDA graph (cached per netlist and tile) and replayed `steps` times; bit
+ * 24 of `mode` says the records carry operand hints (bit 31 of in0 / in1 = "produced two or
+ * more levels back": that fan-in is loaded with an L2 evict-first policy).                               */
 #define MCB_RESIDENT_UNROLL 4
 int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
             const mcb_state *st, int64_t steps, int mode, void *stream);
@@ -148,6 +150,10 @@ int mcb_capture_rows(const int32_t *d_slots, int n, const mcb_state *st, uint64_
  * kind 1 = host to device, 2 = device to host.                                           */
 int mcb_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,
                int64_t width_bytes, int64_t rows, int kind, void *stream);
+
+/* mcb_run mode 1 keeps one instantiated CUDA graph per (netlist, tile geometry, tuning); call
+ * this before freeing the buffers they point into.  Returns the number of graphs dropped.   */
+int mcb_graph_cache_clear(void);
 
 /* tuning knobs (block size, gates per block ...); returns the previous value              */
 int mcb_set_tuning(const char *key, int value);

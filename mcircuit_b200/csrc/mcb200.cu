@@ -13,6 +13,9 @@
 #include <string.h>
 #include <stdarg.h>
 #include <atomic>
+#include <mutex>
+#include <string>
+#include <unordered_map>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -55,13 +58,13 @@ struct Tuning {
     int level_block = 128;      // threads per CTA of the level kernel (128 measured best)
     int level_unroll = 2;       // records in flight per thread (1, 2, 4 or 8); 2 measured best
     int level_ctas_per_sm = 0;  // 0: one record batch per CTA; n: persistent, grid ~ sms * n
-    int level_cache = 1;        // 0: default loads, 1: L1::no_allocate loads
+    int level_cache = 1;        // 0: default loads, 1: L1::no_allocate, 2: + L2 hints (hinted records!)
     int resident_block = 128;   // threads per CTA of the resident kernel
     int resident_tma = 1;       // stage the record stream with cp.async.bulk + mbarrier
     int resident_smem = 1;      // keep state in shared memory when it fits
     int resident_word_bytes = 0;  // bytes of a lane column per thread (0: auto, 8, 4, 2, 1)
     int resident_prefetch = 1;  // prefetch the fan-in rows two batches ahead
-    int graph_min_steps = 2;    // mode 1: capture a graph when steps >= this
+    int graph_min_steps = 1;    // mode 1: replay a cached CUDA graph when steps >= this (and a real stream)
     int persist_unroll = 2;     // records per thread batch of the persistent level kernel
     int persist_hints = 1;      // honour the operand streaming hints (bit 31)
     int persist_ctas_per_sm = 1;  // 0: as many as fit
@@ -69,6 +72,15 @@ struct Tuning {
 };
 static Tuning g_tune;
 static int g_sm_count = 0;
+
+// cached step graphs of mcb_run mode 1 (host-side handles only; they remember pointers)
+struct GraphEntry { cudaGraphExec_t exec; long long nodes; };
+static std::mutex g_graph_mu;
+static std::unordered_map<std::string, GraphEntry> g_graphs;
+static void clear_graphs_locked() {
+    for (auto &kv : g_graphs) cudaGraphExecDestroy(kv.second.exec);
+    g_graphs.clear();
+}
 
 static int sm_count() {
     if (g_sm_count == 0) {
@@ -158,6 +170,29 @@ __device__ __forceinline__ void st_state2(uint64_t *p, ulonglong2 v) {
     asm volatile("st.global.v2.u64 [%0], {%1, %2};" :: "l"(p), "l"(v.x), "l"(v.y) : "memory");
 }
 
+__device__ __forceinline__ uint64_t make_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t make_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ ulonglong2 ld_state2_hint(const uint64_t *p, uint64_t policy) {
+    ulonglong2 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
+                 : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ void st_state2_hint(uint64_t *p, ulonglong2 v, uint64_t policy) {
+    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;"
+                 :: "l"(p), "l"(v.x), "l"(v.y), "l"(policy) : "memory");
+}
+
+#define SLOT_MASK 0x7fffffffu
+
 // ------------------------------------------------------------------------------------------
 // K1: one level.  Thread = one 16-byte column pair; grid.x covers the tile's columns,
 // grid.y strides over the level's records U at a time.  All 2U (3U) row loads of a batch are
@@ -171,6 +206,11 @@ k_eval_level(const uint4 *__restrict__ recs, int n_recs, View v, long long n_vec
     const long long col = ((long long)blockIdx.x * blockDim.x + threadIdx.x);
     if (col >= n_vec) return;
     const long long off = col * 2;
+    // CACHE == 2: the record stream carries operand hints (bit 31 of in0 / in1 = produced two or
+    // more levels back): such fan-in streams through L2 with evict-first so that it does not
+    // push out the previous level's rows, which the next level is about to read
+    uint64_t pol_stream = 0, pol_keep = 0;
+    if (CACHE == 2) { pol_stream = make_policy_evict_first(); pol_keep = make_policy_evict_last(); }
     for (int g0 = blockIdx.y * U; g0 < n_recs; g0 += gridDim.y * U) {
         uint4 r[U];
         ulonglong2 a[U], b[U], c[U];
@@ -183,9 +223,18 @@ k_eval_level(const uint4 *__restrict__ recs, int n_recs, View v, long long n_vec
             const uint32_t op = r[u].x & 0x7f;
             a[u] = b[u] = c[u] = make_ulonglong2(0, 0);
             if (op != MCB_OP_NOP) {
-                a[u] = ld_state2<CACHE>(row(v, r[u].y) + off);
-                if (op != MCB_OP_BUF) b[u] = ld_state2<CACHE>(row(v, r[u].z) + off);
-                if (op >= MCB_OP_MUX) c[u] = ld_state2<CACHE>(row(v, r[u].x >> 8) + off);
+                if (CACHE == 2) {
+                    a[u] = ld_state2_hint(row(v, r[u].y & SLOT_MASK) + off, (r[u].y >> 31) ? pol_stream : pol_keep);
+                    if (op != MCB_OP_BUF)
+                        b[u] = ld_state2_hint(row(v, r[u].z & SLOT_MASK) + off, (r[u].z >> 31) ? pol_stream : pol_keep);
+                    if (op >= MCB_OP_MUX) c[u] = ld_state2<1>(row(v, r[u].x >> 8) + off);
+                    r[u].y &= SLOT_MASK;
+                    r[u].z &= SLOT_MASK;
+                } else {
+                    a[u] = ld_state2<CACHE>(row(v, r[u].y) + off);
+                    if (op != MCB_OP_BUF) b[u] = ld_state2<CACHE>(row(v, r[u].z) + off);
+                    if (op >= MCB_OP_MUX) c[u] = ld_state2<CACHE>(row(v, r[u].x >> 8) + off);
+                }
             }
         }
 #pragma unroll
@@ -222,13 +271,15 @@ static void launch_level_t(const uint4 *recs, int n, const View &v, cudaStream_t
     k_eval_level<U, CACHE><<<grid, block, 0, s>>>(recs, n, v, n_vec);
 }
 
-static int launch_level(const uint4 *recs, int n, const View &v, cudaStream_t s) {
+static int launch_level(const uint4 *recs, int n, const View &v, cudaStream_t s, bool hinted = false) {
     if (n <= 0) return 0;
     const int U = g_tune.level_unroll;
-    const int C = g_tune.level_cache ? 1 : 0;
+    // hinted records MUST go through the variant that masks bit 31 of the operands
+    const int C = hinted ? 2 : (g_tune.level_cache >= 2 ? 1 : g_tune.level_cache);
 #define MCB_LL(UU)                                                                         \
     do {                                                                                   \
-        if (C) launch_level_t<UU, 1>(recs, n, v, s);                                       \
+        if (C >= 2) launch_level_t<UU, 2>(recs, n, v, s);                                  \
+        else if (C == 1) launch_level_t<UU, 1>(recs, n, v, s);                             \
         else launch_level_t<UU, 0>(recs, n, v, s);                                         \
     } while (0)
     if (U >= 8) MCB_LL(8);
@@ -251,28 +302,6 @@ static int launch_level(const uint4 *recs, int n, const View &v, cudaStream_t s)
 // policy for the streaming fan-in so it does not push the recent rows out.  Loads never
 // allocate in L1 (it is not coherent across SMs within a launch).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint64_t make_policy_evict_first() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ uint64_t make_policy_evict_last() {
-    uint64_t p;
-    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-    return p;
-}
-__device__ __forceinline__ ulonglong2 ld_state2_hint(const uint64_t *p, uint64_t policy) {
-    ulonglong2 r;
-    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v2.u64 {%0, %1}, [%2], %3;"
-                 : "=l"(r.x), "=l"(r.y) : "l"(p), "l"(policy));
-    return r;
-}
-__device__ __forceinline__ void st_state2_hint(uint64_t *p, ulonglong2 v, uint64_t policy) {
-    asm volatile("st.global.L2::cache_hint.v2.u64 [%0], {%1, %2}, %3;"
-                 :: "l"(p), "l"(v.x), "l"(v.y), "l"(policy) : "memory");
-}
-
-#define SLOT_MASK 0x7fffffffu
 
 // ------------------------------------------------------------------------------------------
 // K1g / K1pp: level kernels on the GROUPED record stream (per level, records sorted by base
@@ -955,8 +984,8 @@ int mcb_device_info(int device, int *sms, int *cc_major, int *cc_minor, int64_t 
     return 0;
 }
 
-int mcb_eval_levels(const uint32_t *d_records, const int32_t *h_level_off, int level_begin,
-                    int level_end, const mcb_state *st, void *stream) {
+static int eval_levels_impl(const uint32_t *d_records, const int32_t *h_level_off, int level_begin,
+                            int level_end, const mcb_state *st, void *stream, bool hinted) {
     int rc = check_state(st);
     if (rc) return rc;
     if (!d_records || !h_level_off || level_begin < 0 || level_end < level_begin)
@@ -965,10 +994,15 @@ int mcb_eval_levels(const uint32_t *d_records, const int32_t *h_level_off, int l
     const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
     for (int l = level_begin; l < level_end; ++l) {
         const int lo = h_level_off[l], hi = h_level_off[l + 1];
-        rc = launch_level(recs + lo, hi - lo, v, (cudaStream_t)stream);
+        rc = launch_level(recs + lo, hi - lo, v, (cudaStream_t)stream, hinted);
         if (rc) return rc;
     }
     return 0;
+}
+
+int mcb_eval_levels(const uint32_t *d_records, const int32_t *h_level_off, int level_begin,
+                    int level_end, const mcb_state *st, void *stream) {
+    return eval_levels_impl(d_records, h_level_off, level_begin, level_end, st, stream, false);
 }
 
 int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void *stream) {
@@ -990,6 +1024,7 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
     const View v = make_view(st);
     const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
     const int unroll = (mode >> 8) & 0xff, word_bytes = (mode >> 16) & 0xff;
+    const bool hinted = (mode >> 24) & 1;      // mode 1: the records carry operand hints (bit 31)
     mode &= 0xff;
     if (mode == 0) {
         const int u = unroll ? unroll : MCB_RESIDENT_UNROLL;
@@ -1001,36 +1036,66 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
     if (mode != 1) return fail(MCB_ERR_ARG, "unknown mode %d", mode);
     if (steps < g_tune.graph_min_steps || s == nullptr) {
         for (int64_t t = 0; t < steps; ++t) {
-            rc = mcb_eval_levels(d_records, h_level_off, 0, n_levels, st, stream);
+            rc = eval_levels_impl(d_records, h_level_off, 0, n_levels, st, stream, hinted);
             if (rc) return rc;
         }
         return 0;
     }
-    // capture one step once, replay it `steps` times: no host round trip per level
-    cudaGraph_t graph = nullptr;
+    // One step = one CUDA graph (a kernel node per level), captured once per (netlist, tile
+    // geometry, tuning) and kept: replaying it costs one launch call per step and the levels
+    // follow each other on the device without waiting for the host.
+    std::string key;
+    {
+        uint64_t h = 1469598103934665603ull;                       // FNV-1a of the level table
+        for (int l = 0; l <= n_levels; ++l) { h ^= (uint64_t)(uint32_t)h_level_off[l]; h *= 1099511628211ull; }
+        const int tune[4] = {g_tune.level_block, g_tune.level_unroll, g_tune.level_ctas_per_sm, g_tune.level_cache};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        key.append((const char *)&d_records, sizeof(d_records));
+        key.append((const char *)&h, sizeof(h));
+        key.append((const char *)&n_levels, sizeof(n_levels));
+        key.append((const char *)st, sizeof(*st));
+        key.append((const char *)tune, sizeof(tune));
+        key.append((const char *)&dev, sizeof(dev));
+        key.push_back(hinted ? 'h' : 'p');
+    }
     cudaGraphExec_t exec = nullptr;
-    const long long before = g_launches.load();
-    CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    rc = mcb_eval_levels(d_records, h_level_off, 0, n_levels, st, stream);
-    cudaError_t e = cudaStreamEndCapture(s, &graph);
-    const long long per_step = g_launches.load() - before;   // nodes captured, nothing ran yet
-    g_launches.store(before);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return fail(MCB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    if (e != cudaSuccess) {
+    long long per_step = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_graph_mu);
+        auto it = g_graphs.find(key);
+        if (it != g_graphs.end()) { exec = it->second.exec; per_step = it->second.nodes; }
+    }
+    if (!exec) {
+        cudaGraph_t graph = nullptr;
+        const long long before = g_launches.load();
+        CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        rc = eval_levels_impl(d_records, h_level_off, 0, n_levels, st, stream, hinted);
+        cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        per_step = g_launches.load() - before;             // nodes captured, nothing ran yet
+        g_launches.store(before);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return fail(MCB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
-        return fail(MCB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+        if (ce != cudaSuccess) return fail(MCB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
+        std::lock_guard<std::mutex> lock(g_graph_mu);
+        if (g_graphs.size() >= 4096) clear_graphs_locked();
+        g_graphs[key] = GraphEntry{exec, per_step};
     }
     for (int64_t t = 0; t < steps; ++t) {
-        e = cudaGraphLaunch(exec, s);
-        if (e != cudaSuccess) break;
+        cudaError_t le = cudaGraphLaunch(exec, s);
+        if (le != cudaSuccess) return fail(MCB_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(le));
         g_launches.fetch_add(per_step, std::memory_order_relaxed);
     }
-    cudaGraphExecDestroy(exec);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(MCB_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(e));
     return 0;
+}
+
+int mcb_graph_cache_clear(void) {
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    const int n = (int)g_graphs.size();
+    clear_graphs_locked();
+    return n;
 }
 
 int mcb_run_pipelined(const uint32_t *d_records, const int32_t *d_level_off,

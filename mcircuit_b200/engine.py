@@ -27,8 +27,8 @@ from .runtime import MODE_LEVELS, MODE_RESIDENT, RESIDENT_UNROLL
 SEED = 0x6D63697263756974      # "mcircuit"
 _ALL = 0xFFFFFFFFFFFFFFFF
 _ALIGN_WORDS = 16              # rows start on 128-byte boundaries
-DEFAULT_TILE_WORDS = 1280      # 10 KB rows x 3 streams: best measured (profiles/r01_sweep_streams.jsonl)
-DEFAULT_STREAMS = 3
+DEFAULT_TILE_WORDS = 512       # 4 KB rows: a level's rows (20 MB for C5) survive in L2 until the next level
+DEFAULT_STREAMS = 2            # two tiles interleaved; best measured (profiles/r01_sweep_streams_graphs_honest.jsonl)
 
 
 def _round_up(x, m):
@@ -73,7 +73,7 @@ class B200Engine(Executor):
                  keep="auto", observe: Sequence[str] = (), tile_words: Optional[int] = None,
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
-                 resident_word_bytes=0, in_flight=2, streams=None):
+                 resident_word_bytes=0, in_flight=2, streams=None, level_hints=False):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -121,7 +121,7 @@ class B200Engine(Executor):
             if fits and not (wide and self.n_streams > 1 and self.words > 2 * DEFAULT_TILE_WORDS):
                 tile_words = self.words                      # everything resident, one tile
             else:
-                # wide level sweeps run best as ~10 KB-row tiles alternating over a few streams
+                # wide level sweeps run best as small tiles (L2-resident levels) alternating over 2 streams
                 room = max(budget - persist_bytes, 0)
                 planes = max(self.n_streams, self.in_flight)
                 tile_words = max(_ALIGN_WORDS, min(DEFAULT_TILE_WORDS,
@@ -157,7 +157,9 @@ class B200Engine(Executor):
             self.scratch_stride = _round_up(tile_words, _ALIGN_WORDS)
             planes = self.in_flight if mode == "persistent" else self.n_streams
             self._scratch = self.rt.zeros_words(planes * S * self.scratch_stride + _ALIGN_WORDS)
-        self._d_records = self.rt.to_device(program.records)
+        # level mode streams old fan-in through L2 with evict-first (hint bit 31 of in0 / in1)
+        self.level_hints = bool(level_hints) and getattr(program, "records_hinted", None) is not None
+        self._d_records = self.rt.to_device(program.records_hinted if self.level_hints else program.records)
         self._h_level_off = np.ascontiguousarray(program.level_off, dtype=np.int32)
         self._resident = None      # (d_records in batches, h_level_off), built on first use
         # resident kernel: records per batch (4, 8, 16) and bytes of a lane word per thread (0 = auto)
@@ -171,6 +173,18 @@ class B200Engine(Executor):
 
         for base, width, value in program.constants:           # simulator.py:275-276
             self._poke_signals(base, width, int(value))
+
+    def close(self):
+        """Drop the cached step graphs (they hold raw pointers into this engine's buffers)."""
+        clear = getattr(self.rt, "graph_cache_clear", None)
+        if clear is not None:
+            clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     # ------------------------------------------------------------------------------------------
     # state views
@@ -225,7 +239,7 @@ class B200Engine(Executor):
         if self.mode == "persistent":
             self._run_pipelined(steps)
             return
-        if self.n_streams > 1 and self.n_tiles > 1 and self.mode in ("levels", "levels_grouped"):
+        if hasattr(self.rt, "torch") and self.n_tiles > 1 and self.mode in ("levels", "levels_grouped"):
             torch = self.rt.torch
             main = torch.cuda.current_stream(self.rt.device)
             streams = self._compute_streams()
@@ -292,7 +306,8 @@ class B200Engine(Executor):
                             MODE_RESIDENT | (self.resident_batch << 8) | (self.resident_word_bytes << 16))
         else:
             self.rt.run(self._d_records, self._h_level_off, self.program.n_levels,
-                        self._state_for(c0, n, plane=plane), steps, MODE_LEVELS)
+                        self._state_for(c0, n, plane=plane), steps,
+                        MODE_LEVELS | ((1 << 24) if self.level_hints else 0))
 
     def run_host(self, in_plan, h_in, out_plan, h_out, steps: int = 1):
         """Host buffers in, host buffers out, pipelined by lane tile: the stimulus rows of
@@ -321,7 +336,7 @@ class B200Engine(Executor):
             ev = torch.cuda.Event()
             ev.record(s_in)
             ready.append(ev)
-        multi = self.n_streams > 1 and len(tiles) > 1 and self.mode in ("levels", "levels_grouped")
+        multi = len(tiles) > 1 and self.mode in ("levels", "levels_grouped")
         comp = self._compute_streams() if multi else [main]
         if multi:
             for cs in comp:

@@ -60,6 +60,7 @@ _PROTOTYPES = [
     ("mcb_unpack", c_int, [c_void_p, c_int, c_void_p, POINTER(McbState), c_void_p]),
     ("mcb_capture_rows", c_int, [c_void_p, c_int, POINTER(McbState), c_void_p, c_int64, c_void_p]),
     ("mcb_copy2d", c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    ("mcb_graph_cache_clear", c_int, []),
     ("mcb_set_tuning", c_int, [c_char_p, c_int]),
     ("mcb_launch_count", c_int64, [c_int]),
 ]
@@ -243,6 +244,9 @@ class CudaRuntime:
 
     def set_tuning(self, key: str, value: int) -> int:
         return self.lib.mcb_set_tuning(key.encode(), int(value))
+
+    def graph_cache_clear(self) -> int:
+        return int(self.lib.mcb_graph_cache_clear())
 
     def launch_count(self, reset=False) -> int:
         return int(self.lib.mcb_launch_count(1 if reset else 0))

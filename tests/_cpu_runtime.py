@@ -146,7 +146,12 @@ class CpuRuntime:
 
     def run(self, d_records, h_level_off, n_levels, st, steps, mode):
         batch = ((mode >> 8) & 0xFF) or 4
+        hinted = (mode >> 24) & 1
         mode &= 0xFF
+        if hinted:
+            d_records = d_records.astype(np.int64)
+            d_records[:, 1] &= 0x7FFFFFFF
+            d_records[:, 2] &= 0x7FFFFFFF
         if mode == 0:
             assert all(int(x) % batch == 0 for x in h_level_off), "resident stream must be padded"
             # batches of records, loads before stores - exactly the kernel's hazard model
