@@ -22,7 +22,7 @@ import numpy as np
 
 from . import compiler
 from .compiler import PinNotObservable, Program
-from .runtime import MODE_LEVELS, MODE_RESIDENT, RESIDENT_UNROLL
+from .runtime import MODE_LEVELS, MODE_RESIDENT
 
 SEED = 0x6D63697263756974      # "mcircuit"
 _ALL = 0xFFFFFFFFFFFFFFFF
@@ -49,23 +49,6 @@ class Executor:
 
     def burst(self):
         raise NotImplementedError
-
-
-def pad_levels(records: np.ndarray, level_off: np.ndarray, unroll: int = RESIDENT_UNROLL):
-    """Pad every level with NOP records to a multiple of ``unroll`` (resident kernel: a
-    batch of ``unroll`` records never straddles a level)."""
-    n_levels = len(level_off) - 1
-    sizes = np.diff(level_off).astype(np.int64)
-    padded = (sizes + unroll - 1) // unroll * unroll
-    new_off = np.zeros(n_levels + 1, dtype=np.int64)
-    np.cumsum(padded, out=new_off[1:])
-    out = np.zeros((int(new_off[-1]), 4), dtype=np.uint32)
-    if len(records):
-        # destination index of each original record
-        lvl = np.repeat(np.arange(n_levels), sizes)
-        dst = np.arange(len(records)) - level_off[:-1].astype(np.int64)[lvl] + new_off[:-1][lvl]
-        out[dst] = records
-    return out, new_off.astype(np.int32)
 
 
 class B200Engine(Executor):

@@ -18,12 +18,6 @@ class _State:
         self.scratch, self.sstride, self.scol = scratch, sstride, scol
         self.n_persist, self.n_slots, self.n_words = n_persist, n_slots, n_words
 
-    def rows(self, slots):
-        """index array [len(slots), n_words] into the right plane, and which plane"""
-        slots = np.asarray(slots, dtype=np.int64)
-        cols = np.arange(self.n_words, dtype=np.int64)
-        return slots, cols
-
     def read(self, slots):
         slots = np.asarray(slots, dtype=np.int64)
         out = np.empty((len(slots), self.n_words), dtype=U64)

@@ -8,7 +8,7 @@ from _cpu_runtime import CpuRuntime
 from _helpers import (build, compare_engine_to_oracle, golden, lane_trick_planes,
                       run_register_case, run_trace_case)
 from mcircuit_b200 import circuits, compiler
-from mcircuit_b200.engine import B200Engine, pad_levels
+from mcircuit_b200.engine import B200Engine
 
 TRACES = golden("traces.json")
 
@@ -209,15 +209,6 @@ def test_levelization_invariants():
                 assert len(writes) == len(r)
                 for slot, k in reads:
                     assert slot not in writes or writes[slot] == k, (seed, keep, lv)
-
-
-def test_pad_levels():
-    rec = np.arange(7 * 4, dtype=np.uint32).reshape(7, 4) + 1
-    off = np.array([0, 3, 3, 7], dtype=np.int32)
-    out, noff = pad_levels(rec, off, 4)
-    assert noff.tolist() == [0, 4, 4, 8]
-    assert np.array_equal(out[:3], rec[:3]) and not out[3].any()
-    assert np.array_equal(out[4:8], rec[3:7])
 
 
 def test_signature_and_stimulus_and_toggles():

@@ -327,3 +327,16 @@ def test_gpu_tiles_on_several_streams(streams):
     torch.cuda.synchronize()
     for k, p in enumerate(b.output_pins()):
         assert np.array_equal(h_out[k].numpy().view(np.uint64), a.get_pin_planes(p)[0]), p
+
+
+def test_reference_side_stub_of_integration_md():
+    """examples/reference_side_stub.py (the binding INTEGRATION.md shows) against the goldens."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("reference_side_stub",
+                                                  os.path.join(root, "examples", "reference_side_stub.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    for case in TRACES[:8] + TRACES[-4:]:
+        run_trace_case(case, lambda r, bs: mod.B200(r, bs, True))
