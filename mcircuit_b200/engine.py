@@ -292,7 +292,7 @@ class B200Engine(Executor):
                         self._state_for(c0, n, plane=plane), steps,
                         MODE_LEVELS | ((1 << 24) if self.level_hints else 0))
 
-    def run_host(self, in_plan, h_in, out_plan, h_out, steps: int = 1):
+    def run_host(self, in_plan, h_in, out_plan, h_out, steps: int = 1, io_chunk_words: int = 4096):
         """Host buffers in, host buffers out, pipelined by lane tile: the stimulus rows of
         tile t+1 are uploaded (copy stream) while tile t is evaluated (compute stream) and
         the result rows of tile t-1 are downloaded (second copy stream).  ``h_in`` /
@@ -311,8 +311,14 @@ class B200Engine(Executor):
         pitch = self.stride * 8
         in_pitch, out_pitch = h_in.stride(0) * 8, h_out.stride(0) * 8
         tiles = list(self._tiles())
+        # I/O moves in chunks of several compute tiles: a strided copy of 4 KB row segments (one
+        # 512-word tile) is descriptor-bound on the DMA engines, 32 KB segments are not
+        per_chunk = max(1, io_chunk_words // max(1, self.tile_words))
+        chunks = [tiles[i:i + per_chunk] for i in range(0, len(tiles), per_chunk)]
         ready = []
-        for c0, n in tiles:
+        for chunk in chunks:
+            c0 = chunk[0][0]
+            n = sum(t[1] for t in chunk)
             for first, count, k in in_plan["runs"]:
                 self.rt.copy2d(base + (first * self.stride + c0) * 8, pitch,
                                h_in.data_ptr() + k * in_pitch + c0 * 8, in_pitch, n * 8, count, True, s_in)
@@ -324,14 +330,23 @@ class B200Engine(Executor):
         if multi:
             for cs in comp:
                 cs.wait_stream(main)
-        for t, ((c0, n), ev) in enumerate(zip(tiles, ready)):
-            cs = comp[t % len(comp)]
-            cs.wait_event(ev)
-            with torch.cuda.stream(cs):
-                self._run_tile(c0, n, steps, plane=(t % len(comp)) if multi else 0)
-            done = torch.cuda.Event()
-            done.record(cs)
-            s_out.wait_event(done)
+        t = 0
+        for chunk, ev in zip(chunks, ready):
+            used = set()
+            for c0, n in chunk:
+                cs = comp[t % len(comp)]
+                if cs not in used:
+                    cs.wait_event(ev)
+                    used.add(cs)
+                with torch.cuda.stream(cs):
+                    self._run_tile(c0, n, steps, plane=(t % len(comp)) if multi else 0)
+                t += 1
+            for cs in used:
+                done = torch.cuda.Event()
+                done.record(cs)
+                s_out.wait_event(done)
+            c0 = chunk[0][0]
+            n = sum(x[1] for x in chunk)
             for first, count, k in out_plan["runs"]:
                 self.rt.copy2d(h_out.data_ptr() + k * out_pitch + c0 * 8, out_pitch,
                                base + (first * self.stride + c0) * 8, pitch, n * 8, count, False, s_out)

@@ -308,3 +308,74 @@ def test_batch_schedule_hazards_and_results(batch):
     compare_engine_to_oracle(lambda M: circuits.lfsr_pipeline(M, 3, 8, 10, taps=(7, 5, 1, 0)),
                              lambda r, bs, lanes: engine_factory("resident", "ports", resident_batch=batch)(r, bs, lanes),
                              lanes=64, steps=30, probes=probes, pokes=pokes)
+
+
+def test_edge_cases_empty_ragged_wide():
+    # empty circuit: nothing to evaluate, stepping is a no-op
+    eng = engine_factory()(MD.Composite(), 3)
+    eng.step()
+    eng.burst()
+    assert eng.steps_done == 5 and eng.program.n_ops == 0 and eng.gate_evals(7) == 0
+    # ports only, wired straight through (pure aliasing, no primitive at all)
+    top = MD.Composite()
+    top.add_child("i", MD.ExposedPin(MD.ExposedPin.IN, 7))
+    top.add_child("o", MD.ExposedPin(MD.ExposedPin.OUT, 7))
+    top.connect("i", "", "o", "")
+    eng = engine_factory()(top, 1)
+    eng.set_pin_state("/i/pin", 0x55)
+    eng.step()
+    assert eng.get_pin_state("/o/pin") == 0x55 and eng.program.n_ops == 0
+    # lanes must be whole 64-lane words
+    for bad in (0, 1, 63, 100):
+        with pytest.raises(ValueError):
+            B200Engine(top, 1, True, lanes=bad, runtime=CpuRuntime())
+    # the widest things the reference's GUI allows (editors.py:108-124): 64 inputs, 64 bits
+    top = MD.Composite()
+    top.add_child("g", MD.Gate(MD.Gate.XOR, 64, 64, True))
+    eng = B200Engine(top, 1, True, lanes=64 * 3, runtime=CpuRuntime())
+    ora = __import__("oracle.restate", fromlist=["x"]).RestatedJIT(top, 1, True, lanes=64 * 3)
+    rng = np.random.default_rng(9)
+    for i in range(64):
+        v = rng.integers(0, 2**63, size=64 * 3, dtype=np.uint64) * np.uint64(2) + np.uint64(i & 1)
+        eng.set_pin_state(f"/g/in{i}", v)
+        ora.set_pin_state(f"/g/in{i}", v)
+    eng.step()
+    ora.step()
+    assert np.array_equal(eng.get_pin_state("/g/out", lanes=True), ora.get_pin_state("/g/out", lanes=True))
+    assert eng.program.n_gates == 64 * 32            # 63 two-input folds become 32 three-input ops per bit
+
+
+def test_deep_hierarchy_and_shared_instances():
+    """The same Composite object under many names and at several depths (instancing by path,
+    examples/raw_counter.py:104-105)."""
+    inv = MD.Composite()
+    inv.add_child("a", MD.ExposedPin(MD.ExposedPin.IN))
+    inv.add_child("n", MD.Not())
+    inv.add_child("y", MD.ExposedPin(MD.ExposedPin.OUT))
+    inv.connect("a", "", "n", "in")
+    inv.connect("n", "out", "y", "")
+    level = inv
+    for depth in range(5):                          # wrap: two instances of the previous level in series
+        w = MD.Composite()
+        w.add_child("a", MD.ExposedPin(MD.ExposedPin.IN))
+        w.add_child("u", level)
+        w.add_child("v", level)
+        w.add_child("y", MD.ExposedPin(MD.ExposedPin.OUT))
+        w.connect("a", "", "u", "a")
+        w.connect("u", "y", "v", "a")
+        w.connect("v", "y", "y", "")
+        level = w
+    top = MD.Composite()
+    top.add_child("x", MD.ExposedPin(MD.ExposedPin.IN))
+    top.add_child("c", level)
+    top.add_child("z", MD.ExposedPin(MD.ExposedPin.OUT))
+    top.connect("x", "", "c", "a")
+    top.connect("c", "y", "z", "")
+    eng = engine_factory("levels", "all")(top, 1)
+    assert eng.program.n_gates == 32 and eng.program.n_levels == 32      # 2^5 inverters in series
+    for v in (0, 1):
+        eng.set_pin_state("/x/pin", v)
+        eng.step()
+        assert eng.get_pin_state("/z/pin") == v                           # even number of inverters
+        assert eng.get_pin_state("/c/u/u/u/u/u/n/out") == 1 - v           # the very first inverter
+        assert eng.get_pin_state("/c/v/v/v/v/v/y/pin") == v

@@ -206,10 +206,12 @@ def test_gpu_run_host_pipelined_matches_resident():
     h_out = torch.zeros((out_plan["n"], b.words), dtype=torch.int64, pin_memory=True)
     stim = restate.stimulus_word(np.arange(48)[:, None], np.arange(b.words)[None, :])
     h_in.numpy()[:] = stim.view(np.int64)
-    b.run_host(in_plan, h_in, out_plan, h_out)
-    torch.cuda.synchronize()
-    for k, p in enumerate(b.output_pins()):
-        assert np.array_equal(h_out[k].numpy().view(np.uint64), a.get_pin_planes(p)[0]), p
+    for chunk_words in (4096, 64, 32):                 # one I/O chunk, chunks of 2 tiles, of 1 tile
+        h_out.zero_()
+        b.run_host(in_plan, h_in, out_plan, h_out, io_chunk_words=chunk_words)
+        torch.cuda.synchronize()
+        for k, p in enumerate(b.output_pins()):
+            assert np.array_equal(h_out[k].numpy().view(np.uint64), a.get_pin_planes(p)[0]), (chunk_words, p)
     pa, ca = a.signature()
     pb, cb = b.signature()
     assert np.array_equal(pa, pb) and np.array_equal(ca, cb)
@@ -323,10 +325,12 @@ def test_gpu_tiles_on_several_streams(streams):
     h_in = torch.empty((in_plan["n"], b.words), dtype=torch.int64, pin_memory=True)
     h_out = torch.zeros((out_plan["n"], b.words), dtype=torch.int64, pin_memory=True)
     h_in.numpy()[:] = restate.stimulus_word(np.arange(64)[:, None], np.arange(b.words)[None, :]).view(np.int64)
-    b.run_host(in_plan, h_in, out_plan, h_out)
-    torch.cuda.synchronize()
-    for k, p in enumerate(b.output_pins()):
-        assert np.array_equal(h_out[k].numpy().view(np.uint64), a.get_pin_planes(p)[0]), p
+    for chunk_words in (4096, 96):
+        h_out.zero_()
+        b.run_host(in_plan, h_in, out_plan, h_out, io_chunk_words=chunk_words)
+        torch.cuda.synchronize()
+        for k, p in enumerate(b.output_pins()):
+            assert np.array_equal(h_out[k].numpy().view(np.uint64), a.get_pin_planes(p)[0]), (chunk_words, p)
 
 
 def test_reference_side_stub_of_integration_md():
@@ -340,3 +344,38 @@ def test_reference_side_stub_of_integration_md():
     spec.loader.exec_module(mod)
     for case in TRACES[:8] + TRACES[-4:]:
         run_trace_case(case, lambda r, bs: mod.B200(r, bs, True))
+
+
+def test_gpu_edge_cases_empty_ragged_wide():
+    eng = B200Engine(MD.Composite(), 3, True)
+    eng.step()
+    eng.burst()
+    assert eng.steps_done == 5
+    top = MD.Composite()
+    top.add_child("g", MD.Gate(MD.Gate.XOR, 64, 64, True))
+    lanes = 64 * 3
+    eng = B200Engine(top, 1, True, lanes=lanes)
+    ora = restate.RestatedJIT(top, 1, True, lanes=lanes)
+    rng = np.random.default_rng(9)
+    for i in range(64):
+        v = rng.integers(0, 2**63, size=lanes, dtype=np.uint64) * np.uint64(2) + np.uint64(i & 1)
+        eng.set_pin_state(f"/g/in{i}", v)
+        ora.set_pin_state(f"/g/in{i}", v)
+    eng.step()
+    ora.step()
+    assert np.array_equal(eng.get_pin_state("/g/out", lanes=True), ora.get_pin_state("/g/out", lanes=True))
+    # a single lane word, an odd number of lane words, and a tile boundary that is not a multiple of the tile
+    root = circuits.random_dag(MD, n_gates=900, depth=9, n_inputs=20, seed=31)
+    ref = None
+    for lanes_, kw in ((64, {}), (64 * 37, {}), (64 * 37, {"tile_words": 16, "mode": "levels"}),
+                       (64 * 37, {"tile_words": 16, "mode": "persistent"}), (64 * 37, {"mode": "resident"})):
+        e = B200Engine(root, 1, True, lanes=lanes_, keep="ports", **kw)
+        e.randomize_inputs()
+        e.step()
+        planes = np.stack([e.get_pin_planes(p)[0] for p in e.output_pins()])
+        if lanes_ == 64 * 37:
+            if ref is None:
+                ref = planes
+            assert np.array_equal(planes, ref), kw
+        else:
+            assert ref is None or np.array_equal(planes[:, :1], ref[:, :1])
