@@ -187,6 +187,19 @@ def main():
             "c5_random_dag_%d" % gates, "random_dag",
             {"n_gates": gates, "depth": depth, "n_inputs": nin, "seed": seed},
             [f"/i{k}/pin" for k in range(nin)], [f"/o{k}/pin" for k in range(gates // depth)], 4, seed))
+    if "--full-c3" in sys.argv:
+        # the whole C3 netlist on the reference JIT: ~2.5 minutes of JIT build
+        lane.append(case_lane_trick(
+            "c3_array_multiplier64", "array_multiplier", {"n": 64},
+            [f"/a{i}/pin" for i in range(64)] + [f"/b{i}/pin" for i in range(64)],
+            [f"/p{i}/pin" for i in range(128)], 2, 64))
+    else:
+        # keep the committed full-size case when it is not being regenerated
+        try:
+            with open(os.path.join(OUT, "lane_trick.json")) as f:
+                lane += [c for c in json.load(f) if c["name"] == "c3_array_multiplier64"]
+        except OSError:
+            pass
     with open(os.path.join(OUT, "lane_trick.json"), "w") as f:
         json.dump(lane, f, separators=(",", ":"))
     print("lane_trick.json:", len(lane), "cases")

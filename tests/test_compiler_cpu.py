@@ -76,7 +76,7 @@ def test_engine_lane_trick(case, tile_words):
     ins, outs = lane_trick_planes(case)
     nw = case["n_words"]
     # replicate the words so that several tiles exist when tiling is forced
-    reps = 1 if tile_words is None else 5
+    reps = 1 if tile_words is None else max(5, -(-40 // nw))
     eng = B200Engine(build(case), 1, True, lanes=64 * nw * reps, runtime=CpuRuntime(), mode="levels",
                      keep="ports", tile_words=tile_words)
     if tile_words is not None:
