@@ -193,11 +193,16 @@ def main():
             "c3_array_multiplier64", "array_multiplier", {"n": 64},
             [f"/a{i}/pin" for i in range(64)] + [f"/b{i}/pin" for i in range(64)],
             [f"/p{i}/pin" for i in range(128)], 2, 64))
+        # the C5 generator at 10^4 gates: ~2 minutes of JIT build, the practical limit
+        args = {"n_gates": 10000, "depth": 50, "n_inputs": 256, "seed": 13}
+        lane.append(case_lane_trick(
+            "c5_random_dag_10000", "random_dag", args,
+            [f"/i{k}/pin" for k in range(256)], [f"/o{k}/pin" for k in range(200)], 2, 5))
     else:
-        # keep the committed full-size case when it is not being regenerated
+        # keep the committed slow cases when they are not being regenerated
         try:
             with open(os.path.join(OUT, "lane_trick.json")) as f:
-                lane += [c for c in json.load(f) if c["name"] == "c3_array_multiplier64"]
+                lane += [c for c in json.load(f) if c["name"] in ("c3_array_multiplier64", "c5_random_dag_10000")]
         except OSError:
             pass
     with open(os.path.join(OUT, "lane_trick.json"), "w") as f:
