@@ -379,3 +379,42 @@ def test_gpu_edge_cases_empty_ragged_wide():
             assert np.array_equal(planes, ref), kw
         else:
             assert ref is None or np.array_equal(planes[:, :1], ref[:, :1])
+
+
+def test_gpu_c_abi_entry_points_directly(cuda_rt):
+    """mcb_eval_levels, mcb_latch, mcb_fill_rows, mcb_capture_rows and mcb_copy2d called the way
+    a foreign host would: raw device pointers + sizes, no engine in between."""
+    import torch
+    rt = cuda_rt
+    # netlist: level 0: s2 = s0 & s1, s3 = s0 ^ s1 ; level 1: s4 = ~(s2 | s3) ; latch: s5 = s4
+    recs = np.array([[compiler.OP_AND, 0, 1, 2], [compiler.OP_XOR, 0, 1, 3],
+                     [compiler.OP_OR | compiler.OP_NEG, 2, 3, 4]], dtype=np.uint32)
+    latch = np.array([[compiler.OP_BUF, 4, 0, 5]], dtype=np.uint32)
+    off = np.array([0, 2, 3], dtype=np.int32)
+    words, stride, n_slots = 37, 48, 6
+    plane = rt.zeros_words(n_slots * stride)
+    st = rt.make_state(plane, stride, None, 0, n_slots, n_slots, words)
+    rng = np.random.default_rng(0)
+    a = rng.integers(0, 2**63, size=words, dtype=np.uint64)
+    b = rng.integers(0, 2**63, size=words, dtype=np.uint64)
+    h = torch.zeros((2, words), dtype=torch.int64).pin_memory()
+    h.numpy()[0] = a.view(np.int64)
+    h.numpy()[1] = b.view(np.int64)
+    rt.copy2d(plane.data_ptr(), stride * 8, h.data_ptr(), words * 8, words * 8, 2, True)        # H2D rows 0, 1
+    d_recs, d_latch = rt.to_device(recs), rt.to_device(latch)
+    rt.eval_levels(d_recs, off, 0, 2, st)
+    rt.latch(d_latch, 1, st)
+    out = torch.zeros((2, words), dtype=torch.int64).pin_memory()
+    rt.copy2d(out.data_ptr(), words * 8, plane.data_ptr() + 4 * stride * 8, stride * 8, words * 8, 2, False)
+    cap = rt.zeros_words(2 * 64)
+    rt.capture_rows(rt.to_device(np.array([2, 3], dtype=np.int32)), 2, st, cap, 0, 64)
+    rt.synchronize()
+    want = ~((a & b) | (a ^ b))
+    assert np.array_equal(out.numpy().view(np.uint64)[0], want)               # slot 4
+    assert np.array_equal(out.numpy().view(np.uint64)[1], want)               # slot 5, latched copy
+    c = rt.to_host_u64(cap).reshape(2, 64)[:, :words]
+    assert np.array_equal(c[0], a & b) and np.array_equal(c[1], a ^ b)
+    # argument validation reaches the caller as an exception with the library's message
+    bad = rt.make_state(plane, stride - 1, None, 0, n_slots, n_slots, words)    # odd stride
+    with pytest.raises(RuntimeError, match="strides must be even"):
+        rt.eval_levels(d_recs, off, 0, 2, bad)
