@@ -411,6 +411,7 @@ class _Ops:
         self.n_sig = n_signals
         self.first_temp = n_signals
         self.allow3 = allow3
+        self.dead = set()                 # pin signals orphaned by edge-detector sharing
 
     def temp(self) -> int:
         t = self.n_sig
@@ -470,18 +471,22 @@ def _lower_clock(ops, desc, out):
     ops.emit(OP_BUF | OP_NEG, out[0], out[0])        # out = ~out, simulator.py:130-132
 
 
-def _lower_counter(ops, desc, clock, out, prevclock):
+def _lower_counter(ops, desc, clock, out, prevclock, shared_rise=None):
     # rise = ~prevclock & clock, zero-extended: only bit 0 of `out` is ever muxed
     # (simulator.py:100-112); bits 1.. hold.  prevclock = clock, re-read last.
+    if shared_rise is not None:
+        ops.emit(OP_XOR, out[0], out[0], shared_rise)
+        return shared_rise
     rise = ops.emit(OP_ANDN, ops.temp(), clock[0], prevclock[0])
     ops.emit(OP_XOR, out[0], out[0], rise)
     ops.emit(OP_BUF, prevclock[0], clock[0])
+    return rise
 
 
-def _lower_register(ops, desc, clock, data, out, prevclock):
+def _lower_register(ops, desc, clock, data, out, prevclock, shared_rise=None):
     # Intended semantics of simulator.py:115-127 (the reference's emitter does not
     # compile): out = rise ? data : out ; prevclock = clock.
-    rise = ops.emit(OP_ANDN, ops.temp(), clock[0], prevclock[0])
+    rise = shared_rise if shared_rise is not None else ops.emit(OP_ANDN, ops.temp(), clock[0], prevclock[0])
     for bit in range(len(out)):
         if ops.allow3:
             ops.emit(OP_MUX, out[bit], rise, data[bit], out[bit])
@@ -489,7 +494,9 @@ def _lower_register(ops, desc, clock, data, out, prevclock):
             t1 = ops.emit(OP_AND, ops.temp(), rise, data[bit])
             t2 = ops.emit(OP_ANDN, ops.temp(), out[bit], rise)
             ops.emit(OP_OR, out[bit], t1, t2)
-    ops.emit(OP_BUF, prevclock[0], clock[0])
+    if shared_rise is None:
+        ops.emit(OP_BUF, prevclock[0], clock[0])
+    return rise
 
 
 def _lower_adder(ops, desc, cin, a, b, cout, sum_):
@@ -550,11 +557,40 @@ def _lower_adder(ops, desc, cin, a, b, cout, sum_):
         ops.emit(OP_OR, cout[0], ovf1, ovf2)
 
 
-def lower(design: Design, allow3: bool = True) -> _Ops:
+def lower(design: Design, allow3: bool = True, share_edge_detectors: bool = False) -> _Ops:
+    """``share_edge_detectors``: Registers / Counters that read the same clock net in the same
+    epoch (all before, or all after, the op that writes it) compute the same ``rise`` and hold
+    the same ``prevclock`` for ever, so one ANDN + one BUF serve the whole group and the
+    members' ``prevclock`` pins become views of the leader's bit.  Exact unless a member's
+    ``prevclock`` is poked individually (a poke then reaches the whole group) - hence opt-in."""
     ops = _Ops(design.n_signals, allow3)
     net_sig = design.net_sig
     pin_net = design.pin_net
     pin_width = design.pin_width
+    groups: Dict[Tuple[int, bool], Tuple[int, int]] = {}       # (clock signal, already written) -> (rise, prevclock)
+    written = set()
+    n_seen = 0
+    pins_per_net = np.bincount(pin_net, minlength=len(design.net_width)) if share_edge_detectors else None
+
+    def clocked(leaf, lower_fn, p, *mid):
+        """Lower a Register / Counter, sharing the edge detector of its clock group."""
+        if not share_edge_detectors:
+            lower_fn(ops, design.leaf_desc[leaf], p["clock"], *mid, p["prevclock"])
+            return
+        prev_pin = design.leaf_pin_base[leaf] + design.leaf_table[leaf].index["prevclock"]
+        alone = pins_per_net[pin_net[prev_pin]] == 1            # nothing else wired to prevclock
+        key = (p["clock"][0], p["clock"][0] in written)
+        hit = groups.get(key) if alone else None
+        if hit is not None:
+            rise, leader_prev = hit
+            ops.dead.add(p["prevclock"][0])
+            net_sig[pin_net[prev_pin]] = leader_prev            # the pin now views the leader's bit
+            lower_fn(ops, design.leaf_desc[leaf], p["clock"], *mid, range(leader_prev, leader_prev + 1),
+                     shared_rise=rise)
+        else:
+            rise = lower_fn(ops, design.leaf_desc[leaf], p["clock"], *mid, p["prevclock"])
+            if alone:
+                groups[key] = (rise, p["prevclock"][0])
 
     def sig(pin: int) -> range:
         base = int(net_sig[pin_net[pin]])
@@ -586,14 +622,17 @@ def lower(design: Design, allow3: bool = True) -> _Ops:
             _lower_clock(ops, desc, pins(arg)["out"])
         elif tname == "Counter":
             p = pins(arg)
-            _lower_counter(ops, desc, p["clock"], p["out"], p["prevclock"])
+            clocked(arg, _lower_counter, p, p["out"])
         elif tname == "Register":
             p = pins(arg)
-            _lower_register(ops, desc, p["clock"], p["data"], p["out"], p["prevclock"])
+            clocked(arg, _lower_register, p, p["data"], p["out"])
         elif tname == "Adder":
             p = pins(arg)
             _lower_adder(ops, desc, p["cin"], p["a"], p["b"], p["cout"], p["sum"])
         # ExposedPin, Constant and anything not in TRANSLATOR emit nothing (:214-221)
+        if share_edge_detectors:
+            written.update(ops.out[n_seen:])
+            n_seen = len(ops.out)
     return ops
 
 
@@ -642,7 +681,8 @@ class Program:
 
 
 def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
-                   allow3: Optional[bool] = None, back_edges="auto") -> Program:
+                   allow3: Optional[bool] = None, back_edges="auto",
+                   share_edge_detectors: bool = False) -> Program:
     """Lower, levelize, allocate slots and encode.  ``keep``: 'all' retains every pin net
     (full drop-in observability); 'ports' retains only what a later step or the caller can
     still need - undriven nets (inputs, constants), state, root-level ports and
@@ -657,7 +697,7 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
     latch_slack = {"auto": 1, "order": 1 << 30, "latch": 0}[back_edges]
     if allow3 is None:
         allow3 = design.n_signals * 2 + 1024 < IN2_LIMIT
-    ops = lower(design, allow3)
+    ops = lower(design, allow3, share_edge_detectors)
     n_ops = len(ops.code)
     n_sig = ops.n_sig
     n_pin_sig = ops.first_temp
@@ -731,7 +771,10 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
     # ---- which signals are persistent ------------------------------------------------------
     persistent = bytearray(n_sig)
     kept = np.zeros(n_pin_sig, dtype=bool)
+    dead = ops.dead
     for s in range(n_pin_sig):
+        if s in dead:
+            continue                                    # orphaned by edge-detector sharing
         if keep == "all" or writer[s] == -1 or has_state_read[s]:
             persistent[s] = 1
             kept[s] = True
@@ -809,7 +852,8 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
         raise CircuitError("too many slots")
     if allow3 and n_persist + n_scratch >= IN2_LIMIT:
         # in2 would not fit beside the opcode: redo with 2-input micro-ops only
-        return compile_design(design, keep=keep, observe=observe, allow3=False, back_edges=back_edges)
+        return compile_design(design, keep=keep, observe=observe, allow3=False, back_edges=back_edges,
+                              share_edge_detectors=share_edge_detectors)
 
     # ---- encode ----------------------------------------------------------------------------
     code_a = np.asarray(code, dtype=np.int64)[order]
@@ -954,5 +998,6 @@ def _sig_name(design: Design, s: int) -> str:
 
 
 def compile_circuit(root, map_pins: bool = True, keep="all", observe: Sequence[str] = (),
-                    back_edges="auto") -> Program:
-    return compile_design(flatten(root, map_pins), keep=keep, observe=observe, back_edges=back_edges)
+                    back_edges="auto", share_edge_detectors: bool = False) -> Program:
+    return compile_design(flatten(root, map_pins), keep=keep, observe=observe, back_edges=back_edges,
+                          share_edge_detectors=share_edge_detectors)

@@ -56,7 +56,8 @@ class B200Engine(Executor):
                  keep="auto", observe: Sequence[str] = (), tile_words: Optional[int] = None,
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
-                 resident_word_bytes=0, in_flight=2, streams=None, level_hints=False):
+                 resident_word_bytes=0, in_flight=2, streams=None, level_hints=False,
+                 share_edge_detectors=False):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -77,7 +78,8 @@ class B200Engine(Executor):
             design = compiler.flatten(root, map_pins)
             if keep == "auto":
                 keep = "all" if (design.n_signals * 3 // 2) * self.stride * 8 <= budget // 2 else "ports"
-            program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges)
+            program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges,
+                                              share_edge_detectors=share_edge_detectors)
         self.program = program
         self.keep = keep
         # one extra scratch row that padding records of the resident kernel read and write

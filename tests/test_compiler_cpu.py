@@ -379,3 +379,33 @@ def test_deep_hierarchy_and_shared_instances():
         assert eng.get_pin_state("/z/pin") == v                           # even number of inverters
         assert eng.get_pin_state("/c/u/u/u/u/u/n/out") == 1 - v           # the very first inverter
         assert eng.get_pin_state("/c/v/v/v/v/v/y/pin") == v
+
+
+@pytest.mark.parametrize("mode", ["resident", "levels"])
+def test_shared_edge_detectors_are_exact(mode):
+    """share_edge_detectors=True: one rise / prevclock per clock group, same results on every
+    pin (the members' prevclock pins view the leader's bit)."""
+    args = dict(n_lfsr=3, lfsr_bits=8, stages=10, taps=(7, 5, 1, 0))
+    plain = compiler.compile_circuit(circuits.lfsr_pipeline(MD, **args))
+    shared = compiler.compile_circuit(circuits.lfsr_pipeline(MD, **args), share_edge_detectors=True)
+    n_regs = 3 * 8 + 10
+    assert shared.n_gates == plain.n_gates - 2 * (n_regs - 1)
+    probes = ([f"/tap{n}/pin" for n in range(3)] + ["/pipe_out/pin", "/clk/out"] +
+              [f"/l{n}_q{b}/prevclock" for n in range(3) for b in (0, 3, 7)] + [f"/p{k}/prevclock" for k in (0, 9)] +
+              [f"/l1_q{b}/out" for b in range(8)])
+    pokes = [(f"/l{n}_q{b}/out", (n + b) & 1) for n in range(3) for b in range(8)]
+    compare_engine_to_oracle(lambda M: circuits.lfsr_pipeline(M, **args),
+                             lambda r, bs, lanes: engine_factory(mode, share_edge_detectors=True)(r, bs, lanes),
+                             lanes=64, steps=40, probes=probes, pokes=pokes)
+
+
+@pytest.mark.parametrize("seed", range(400, 430))
+def test_shared_edge_detectors_fuzz(seed):
+    prims = ("Gate", "Not", "Constant", "Clock", "Counter", "Counter", "Adder", "Register", "Register")
+    root, probes = circuits.random_circuit(MD, seed, n_nodes=26, primitives=prims)
+    d = compiler.flatten(root)
+    lane_inputs = [(p, d.pin_width[d.find_pin(p)]) for p in ("/in0/pin", "/in1/pin")]
+    compare_engine_to_oracle(lambda M: circuits.random_circuit(M, seed, n_nodes=26, primitives=prims),
+                             lambda r, bs, lanes: engine_factory(("resident", "levels")[seed % 2],
+                                                                 share_edge_detectors=True)(r, bs, lanes),
+                             lanes=64, steps=8, probes=probes, lane_inputs=lane_inputs, seed=seed)
