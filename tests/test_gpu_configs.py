@@ -178,3 +178,25 @@ def test_c5_signature_is_a_sum_over_shards():
             acc_pc += p
             acc_cs += c
     assert np.array_equal(pc, acc_pc) and np.array_equal(cs, acc_cs)
+
+
+@pytest.mark.parametrize("mode", ["resident", "levels"])
+def test_c4_shared_edge_detectors_vs_oracle(mode):
+    args = dict(n_lfsr=8, lfsr_bits=16, stages=40, taps=(15, 13, 12, 10))
+    root = circuits.lfsr_pipeline(MD, **args)
+    lanes = 256
+    eng = B200Engine(root, 1, True, lanes=lanes, mode=mode, share_edge_detectors=True)
+    ora = cref.CRef(root, 1, True, lanes=lanes)
+    rng = np.random.default_rng(4)
+    for n in range(8):
+        for b in range(16):
+            v = rng.integers(0, 2, size=lanes, dtype=U64)
+            eng.set_pin_state(f"/l{n}_q{b}/out", v)
+            ora.set_pin_state(f"/l{n}_q{b}/out", v)
+    probes = [f"/tap{n}/pin" for n in range(8)] + ["/pipe_out/pin", "/l3_q7/out", "/p17/out", "/p17/prevclock",
+                                                    "/l0_q0/prevclock", "/l7_q15/prevclock"]
+    for chunk in (1, 1, 2, 7, 100):
+        eng.run(chunk)
+        ora.run(chunk)
+        for p in probes:
+            assert np.array_equal(eng.get_pin_planes(p), ora.planes(p)), (chunk, p)
