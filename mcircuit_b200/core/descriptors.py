@@ -33,6 +33,11 @@ class Descriptor:
     _OUTPUTS = ()
     _INTERNALS = ()
 
+    def _set(self, **attributes):
+        """Constructor helper: descriptors are plain attribute bags (the GUI's property editors,
+        editors.py, read and write these attributes by name)."""
+        vars(self).update(attributes)
+
     def clone(self):
         return deepcopy(self)
 
@@ -59,9 +64,7 @@ class ExposedPin(Descriptor):
     OUT = 1
 
     def __init__(self, direction, width=1):
-        super().__init__()
-        self.direction = direction
-        self.width = width
+        self._set(direction=direction, width=width)
 
     def all_inputs(self):
         return iter((("pin", self.width),) if self.direction == ExposedPin.OUT else ())
@@ -77,9 +80,7 @@ class Constant(Descriptor):
     _OUTPUTS = (("out", "width"),)
 
     def __init__(self, width=1, value=0):
-        super().__init__()
-        self.width = width
-        self.value = value
+        self._set(width=width, value=value)
 
 
 class Not(Descriptor):
@@ -89,8 +90,7 @@ class Not(Descriptor):
     _OUTPUTS = (("out", "width"),)
 
     def __init__(self, width=1):
-        super().__init__()
-        self.width = width
+        self._set(width=width)
 
 
 class Gate(Descriptor):
@@ -104,11 +104,7 @@ class Gate(Descriptor):
     _OUTPUTS = (("out", "width"),)
 
     def __init__(self, op, width=1, num_inputs=2, negated=False):
-        super().__init__()
-        self.op = op
-        self.width = width
-        self.num_inputs = num_inputs
-        self.negated = negated
+        self._set(op=op, width=width, num_inputs=num_inputs, negated=negated)
 
     def all_inputs(self):
         return ((f"in{i}", self.width) for i in range(self.num_inputs))
@@ -124,8 +120,7 @@ class Register(Descriptor):
     _INTERNALS = (("prevclock", 1),)
 
     def __init__(self, width=1):
-        super().__init__()
-        self.width = width
+        self._set(width=width)
 
 
 class Counter(Descriptor):
@@ -137,8 +132,7 @@ class Counter(Descriptor):
     _INTERNALS = (("prevclock", 1),)
 
     def __init__(self, width=1):
-        super().__init__()
-        self.width = width
+        self._set(width=width)
 
 
 class Clock(Descriptor):
@@ -149,9 +143,7 @@ class Clock(Descriptor):
     _INTERNALS = (("count", 64),)
 
     def __init__(self):
-        super().__init__()
-        self.short = 1
-        self.long = 1
+        self._set(short=1, long=1)
 
 
 class Adder(Descriptor):
@@ -162,8 +154,7 @@ class Adder(Descriptor):
     _OUTPUTS = (("cout", 1), ("sum", "width"))
 
     def __init__(self, width=1):
-        super().__init__()
-        self.width = width
+        self._set(width=width)
 
 
 class Composite(Descriptor):
@@ -178,9 +169,7 @@ class Composite(Descriptor):
     """
 
     def __init__(self):
-        super().__init__()
-        self.graph = nx.DiGraph()
-        self.connections = set()
+        self._set(graph=nx.DiGraph(), connections=set())
 
     # -- pin-name rewriting (reference descriptors.py:146-152) -------------------------
     def _translate_pin(self, child, pin):
