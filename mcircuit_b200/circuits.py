@@ -159,6 +159,80 @@ def raw_counter(M=_own, bits=2, seed: Optional[int] = 0):
     return main
 
 
+# ---- C4, all-reference variant: LFSR + pipeline out of gate-level flip-flops -------------------
+def gate_level_flipflop(M=_own):
+    """The NOT-loop clock and the master-slave D flip-flop of examples/raw_counter.py:42-92
+    (SR latch -> D latch -> two D latches on opposite clock phases), as composites."""
+    ein, eout = M.ExposedPin(M.ExposedPin.IN), M.ExposedPin(M.ExposedPin.OUT)
+    nor, and_, not_ = M.Gate(M.Gate.OR, negated=True), M.Gate(M.Gate.AND), M.Not()
+    clock = M.Composite()
+    clock.add_child("not", not_)
+    clock.add_child("out", eout)
+    clock.connect("not", "out", "not", "in")
+    clock.connect("not", "out", "out", "")
+    sr = M.Composite()
+    for name, d in (("nor1", nor), ("nor2", nor), ("s", ein), ("r", ein), ("q", eout)):
+        sr.add_child(name, d)
+    sr.connect("nor2", "out", "nor1", "in1")
+    sr.connect("nor1", "out", "nor2", "in0")
+    sr.connect("s", "", "nor2", "in1")
+    sr.connect("r", "", "nor1", "in0")
+    sr.connect("nor1", "out", "q", "")
+    dl = M.Composite()
+    for name, d in (("sr", sr), ("and1", and_), ("and2", and_), ("not", not_), ("d", ein), ("clk", ein), ("q", eout)):
+        dl.add_child(name, d)
+    dl.connect("d", "", "not", "in")
+    dl.connect("not", "out", "and1", "in0")
+    dl.connect("clk", "", "and1", "in1")
+    dl.connect("clk", "", "and2", "in0")
+    dl.connect("d", "", "and2", "in1")
+    dl.connect("and1", "out", "sr", "r")
+    dl.connect("and2", "out", "sr", "s")
+    dl.connect("sr", "q", "q", "")
+    ff = M.Composite()
+    for name, d in (("clk", ein), ("d", ein), ("q", eout), ("not", not_), ("dl1", dl), ("dl2", dl)):
+        ff.add_child(name, d)
+    ff.connect("clk", "", "dl2", "clk")
+    ff.connect("clk", "", "not", "in")
+    ff.connect("not", "out", "dl1", "clk")
+    ff.connect("dl1", "q", "dl2", "d")
+    ff.connect("d", "", "dl1", "d")
+    ff.connect("dl2", "q", "q", "")
+    return clock, ff
+
+
+def gate_level_lfsr(M=_own, n_bits=8, taps=(7, 5, 4, 3), stages=4):
+    """C4's shape with storage the UNMODIFIED reference can run (its Register emitter does not
+    compile): a Fibonacci LFSR of ``n_bits`` gate-level flip-flops (XNOR feedback, so the
+    all-zero reset state is not a fixed point) and a ``stages``-deep flip-flop pipeline fed by
+    XOR(previous stage, lfsr q0).  Ports: /q{i}/pin, /p{k}/pin."""
+    clock, ff = gate_level_flipflop(M)
+    eout = M.ExposedPin(M.ExposedPin.OUT)
+    top = M.Composite()
+    top.add_child("clk", clock)
+    for i in range(n_bits):
+        top.add_child(f"f{i}", ff)
+        top.add_child(f"q{i}", eout)
+    top.add_child("fb", M.Gate(M.Gate.XOR, 1, len(taps), True))
+    for k in range(stages):
+        top.add_child(f"s{k}", ff)
+        top.add_child(f"x{k}", M.Gate(M.Gate.XOR))
+        top.add_child(f"p{k}", eout)
+    for i in range(n_bits):
+        top.connect("clk", "out", f"f{i}", "clk")
+        top.connect(f"f{i - 1}" if i else "fb", "q" if i else "out", f"f{i}", "d")
+        top.connect(f"f{i}", "q", f"q{i}", "")
+    for j, t in enumerate(taps):
+        top.connect(f"f{t}", "q", "fb", f"in{j}")
+    for k in range(stages):
+        top.connect("clk", "out", f"s{k}", "clk")
+        top.connect(f"s{k - 1}" if k else f"f{n_bits - 1}", "q", f"x{k}", "in0")
+        top.connect("f0", "q", f"x{k}", "in1")
+        top.connect(f"x{k}", "out", f"s{k}", "d")
+        top.connect(f"s{k}", "q", f"p{k}", "")
+    return top
+
+
 # ---- C2: n-bit ripple-carry adder of 5-gate full adders -------------------------------------------
 def ripple_adder(M=_own, nbits=32, width=1):
     """Ports: /a{i}/pin, /b{i}/pin, /cin/pin -> /s{i}/pin, /cout/pin.  ``width=64`` is the

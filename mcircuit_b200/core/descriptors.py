@@ -2,8 +2,9 @@
 
 Same class names, constructor signatures, attribute names and generator outputs as the
 reference (``/root/reference/core/descriptors.py:6-180``) so that circuits written against
-mcircuit build unchanged, and so that the reference's own JIT can consume objects made
-here (duck typing) when we pin results against it.  Nothing here touches a GPU.
+mcircuit build unchanged.  (The reference's JIT dispatches on its own classes, so results are
+pinned by building the same circuit twice, once with each module - see
+``mcircuit_b200.circuits``.)  Nothing here touches a GPU.
 
 Pin tables are data (``_INPUTS/_OUTPUTS/_INTERNALS`` specs resolved against ``self``)
 rather than one hand-written generator per class; the observable behaviour is the

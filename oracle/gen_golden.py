@@ -156,6 +156,10 @@ def main():
     cases.append(case_trace("raw_counter_4bit", "raw_counter", {"bits": 4, "seed": 7},
                             ["/b1/q/pin", "/b2/q/pin", "/b3/q/pin", "/b4/q/pin"], 80,
                             pokes=[("/a1/cin/pin", 1)]))
+    # --- C4 as the UNMODIFIED reference can run it: gate-level flip-flops ---
+    cases.append(case_trace("c4_gate_level_lfsr", "gate_level_lfsr", {"n_bits": 8, "taps": [7, 5, 4, 3], "stages": 4},
+                            [f"/q{i}/pin" for i in range(8)] + [f"/p{k}/pin" for k in range(4)] + ["/clk/out/pin"], 200,
+                            note="LFSR + pipeline out of the master-slave flip-flops of examples/raw_counter.py"))
     # --- random circuits: every primitive the reference can compile, feedback, hierarchy -------
     for seed in range(40):
         made, probes = circuits.random_circuit(D, seed, n_nodes=18)
