@@ -682,7 +682,7 @@ class Program:
 
 def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
                    allow3: Optional[bool] = None, back_edges="auto",
-                   share_edge_detectors: bool = False) -> Program:
+                   share_edge_detectors: bool = False, sort_level_by_fanin: bool = False) -> Program:
     """Lower, levelize, allocate slots and encode.  ``keep``: 'all' retains every pin net
     (full drop-in observability); 'ports' retains only what a later step or the caller can
     still need - undriven nets (inputs, constants), state, root-level ports and
@@ -853,7 +853,19 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
     if allow3 and n_persist + n_scratch >= IN2_LIMIT:
         # in2 would not fit beside the opcode: redo with 2-input micro-ops only
         return compile_design(design, keep=keep, observe=observe, allow3=False, back_edges=back_edges,
-                              share_edge_detectors=share_edge_detectors)
+                              share_edge_detectors=share_edge_detectors,
+                              sort_level_by_fanin=sort_level_by_fanin)
+
+    # ---- optional: within a level, order records by the slots of their fan-in -------------------
+    # Records of a level are independent, so their order is free.  Sorting by (in1 slot, in0
+    # slot) makes the CTAs that run side by side read neighbouring rows (DRAM page locality)
+    # and puts gates that share a fan-in row next to each other (the second read hits L2).
+    if sort_level_by_fanin and n_total:
+        b_all = np.asarray(B, dtype=np.int64)
+        a_all = np.asarray(A, dtype=np.int64)
+        sb_all = np.where(b_all >= 0, sig_slot[np.maximum(b_all, 0)], -1)
+        sa_all = np.where(a_all >= 0, sig_slot[np.maximum(a_all, 0)], -1)
+        order = np.lexsort((sa_all, sb_all, level_arr))
 
     # ---- encode ----------------------------------------------------------------------------
     code_a = np.asarray(code, dtype=np.int64)[order]
@@ -998,6 +1010,7 @@ def _sig_name(design: Design, s: int) -> str:
 
 
 def compile_circuit(root, map_pins: bool = True, keep="all", observe: Sequence[str] = (),
-                    back_edges="auto", share_edge_detectors: bool = False) -> Program:
+                    back_edges="auto", share_edge_detectors: bool = False,
+                    sort_level_by_fanin: bool = False) -> Program:
     return compile_design(flatten(root, map_pins), keep=keep, observe=observe, back_edges=back_edges,
-                          share_edge_detectors=share_edge_detectors)
+                          share_edge_detectors=share_edge_detectors, sort_level_by_fanin=sort_level_by_fanin)

@@ -57,7 +57,7 @@ class B200Engine(Executor):
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
                  resident_word_bytes=0, in_flight=2, streams=None, level_hints=False,
-                 share_edge_detectors=False):
+                 share_edge_detectors=False, sort_level_by_fanin=False):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -79,7 +79,8 @@ class B200Engine(Executor):
             if keep == "auto":
                 keep = "all" if (design.n_signals * 3 // 2) * self.stride * 8 <= budget // 2 else "ports"
             program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges,
-                                              share_edge_detectors=share_edge_detectors)
+                                              share_edge_detectors=share_edge_detectors,
+                                              sort_level_by_fanin=sort_level_by_fanin)
         self.program = program
         self.keep = keep
         # one extra scratch row that padding records of the resident kernel read and write

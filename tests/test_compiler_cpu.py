@@ -409,3 +409,21 @@ def test_shared_edge_detectors_fuzz(seed):
                              lambda r, bs, lanes: engine_factory(("resident", "levels")[seed % 2],
                                                                  share_edge_detectors=True)(r, bs, lanes),
                              lanes=64, steps=8, probes=probes, lane_inputs=lane_inputs, seed=seed)
+
+
+def test_sort_level_by_fanin_keeps_levels_and_results():
+    root = circuits.random_dag(MD, n_gates=1200, depth=12, n_inputs=32, seed=6)
+    a = compiler.compile_circuit(root, keep="ports")
+    b = compiler.compile_circuit(root, keep="ports", sort_level_by_fanin=True)
+    assert np.array_equal(a.level_off, b.level_off) and a.n_slots == b.n_slots
+    for lv in range(a.n_levels):
+        ra = a.records[a.level_off[lv]:a.level_off[lv + 1]]
+        rb = b.records[b.level_off[lv]:b.level_off[lv + 1]]
+        assert sorted(map(tuple, ra.tolist())) == sorted(map(tuple, rb.tolist()))     # same records
+        assert (np.diff(rb[:, 2].astype(np.int64)) >= 0).all()                         # ordered by in1 slot
+    ea = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode="levels", program=a)
+    eb = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode="resident", program=b)
+    for e in (ea, eb):
+        e.randomize_inputs()
+        e.step()
+    assert all(np.array_equal(ea.get_pin_planes(p), eb.get_pin_planes(p)) for p in ea.output_pins())
