@@ -13,7 +13,7 @@ from oracle import restate
 ALL_PRIMS = ("Gate", "Not", "Constant", "Clock", "Counter", "Adder", "Register")
 
 
-@settings(max_examples=60, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=60, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(seed=st.integers(0, 10**6), n_nodes=st.integers(2, 28), max_width=st.sampled_from([1, 2, 5, 8, 33, 64]),
        feedback=st.booleans(), hierarchy=st.booleans(), map_pins=st.booleans(),
        keep=st.sampled_from(["all", "ports"]), mode=st.sampled_from(["resident", "levels", "levels_grouped", "persistent"]),
@@ -55,7 +55,7 @@ def test_compiled_program_equals_oracle(seed, n_nodes, max_width, feedback, hier
             pass
 
 
-@settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+@settings(max_examples=40, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
 @given(seed=st.integers(0, 10**6), n_nodes=st.integers(2, 24), max_width=st.sampled_from([1, 3, 8, 31, 64]),
        map_pins=st.booleans())
 def test_c_oracle_equals_numpy_oracle(seed, n_nodes, max_width, map_pins):
