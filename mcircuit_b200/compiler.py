@@ -704,11 +704,40 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
     code, A, B, C, OUT = ops.code, ops.a, ops.b, ops.c, ops.out
 
     # ---- single writer per signal --------------------------------------------------------
+    # The reference happily lets several primitives (or, with map_pins=False, a primitive and a
+    # propagate) store to one global one after the other.  Keep that sequential meaning by
+    # versioning: every write but the LAST of a step goes to a fresh temporary, readers between
+    # two writes are pointed at the version that is live at their place in the sequence, and
+    # the last write lands in the net's own (persistent) signal - which is also what readers
+    # before the first write see: last step's final value.
+    n_writers: Dict[int, int] = {}
+    for o in OUT:
+        n_writers[o] = n_writers.get(o, 0) + 1
+    multi = {s_ for s_, k in n_writers.items() if k > 1}
+    if multi:
+        seen: Dict[int, int] = {}            # writes so far this step
+        live: Dict[int, int] = {}            # signal -> version readers should use now
+        for i in range(n_ops):
+            for arr in (A, B, C):
+                s_ = arr[i]
+                if s_ in live:
+                    arr[i] = live[s_]
+            o = OUT[i]
+            if o in multi:
+                seen[o] = seen.get(o, 0) + 1
+                if seen[o] < n_writers[o]:
+                    v = n_sig
+                    n_sig += 1
+                    OUT[i] = v
+                    live[o] = v
+                else:
+                    live.pop(o, None)        # the final write: readers use the net itself again
+        ops.n_sig = n_sig
     writer = [-1] * n_sig
     for i in range(n_ops):
         o = OUT[i]
         if writer[o] != -1:
-            raise CircuitError("net bit %s has more than one driver" % _sig_name(design, o))
+            raise AssertionError("net bit %s still has more than one driver" % _sig_name(design, o))
         writer[o] = i
 
     # ---- levels: RAW edges, and back reads settled by ordering or by a shadow ----------------

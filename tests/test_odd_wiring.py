@@ -91,7 +91,25 @@ def counter_clocked_by_logic(M):
     return top, ["/g/out", "/c1/out", "/c2/out", "/late/out", "/late/prevclock", "/c1/prevclock"], [("/en/pin", 1)]
 
 
-CASES = [input_pin_as_source, output_pin_as_destination, constant_through_ports, feedback_through_ports,
+def two_primitives_store_to_one_net(M):
+    """b.out is the destination of a.out: both primitives store to one global, one after the
+    other, every step (the reference's globals simply take the writes in emit order)."""
+    top = M.Composite()
+    top.add_child("x", M.ExposedPin(M.ExposedPin.IN, 4))
+    top.add_child("a", M.Not(4))
+    top.add_child("b", M.Gate(M.Gate.XOR, 4))
+    top.add_child("r", M.Not(4))
+    top.add_child("late", M.Gate(M.Gate.OR, 4))
+    top.connect("x", "", "a", "in")
+    top.connect("a", "out", "b", "out")
+    top.connect("x", "", "b", "in0")
+    top.connect("a", "out", "r", "in")
+    top.connect("b", "out", "late", "in0")
+    top.connect("r", "out", "late", "in1")
+    return top, ["/a/out", "/b/out", "/r/out", "/late/out"], [("/x/pin", 0b0110), ("/b/in1", 0b1001)]
+
+
+CASES = [two_primitives_store_to_one_net, input_pin_as_source, output_pin_as_destination, constant_through_ports, feedback_through_ports,
          counter_clocked_by_logic]
 
 
@@ -107,13 +125,6 @@ def _engines(build, map_pins):
 @pytest.mark.parametrize("build", CASES, ids=lambda f: f.__name__)
 @pytest.mark.parametrize("map_pins", [True, False])
 def test_engine_equals_oracle(build, map_pins):
-    if build is output_pin_as_destination and not map_pins:
-        # with one global per pin the reference lets the primitive AND the propagate write g.out
-        # in sequence; two writers of one net bit are rejected here (documented deviation)
-        from mcircuit_b200.compiler import CircuitError
-        with pytest.raises(CircuitError):
-            B200Engine(build(MD)[0], 3, False, runtime=CpuRuntime())
-        return
     sims, probes, pokes = _engines(build, map_pins)
     for step in range(9):
         if step == 4:
