@@ -119,3 +119,21 @@ def test_capture_and_vcd():
     assert "$var wire 1 ! clk.out $end" in vcd and '$var wire 16 " r.out $end' in vcd
     assert '#0\n1!\nb1 "' in vcd and '#2\n1!\nb0 "' in vcd
     assert eng.steps_done == 8
+
+
+def test_netlist_file_loads_into_the_reference_too(reference, tmp_path):
+    """A netlist saved from our descriptors rebuilds with the REFERENCE's descriptor module and
+    runs on its JIT with the same results as our engine on the original."""
+    from oracle import refshim
+    D, _ = reference
+    root, probes = circuits.random_circuit(MD, 77, n_nodes=18)
+    path = tmp_path / "n.json"
+    netlist_io.save(root, path)
+    ref_root = netlist_io.load(path, M=D)
+    jit = refshim.build_jit(ref_root, 3, True)
+    eng = B200Engine(root, 3, True, runtime=CpuRuntime())
+    for step in range(8):
+        jit.step()
+        eng.step()
+        for p in probes:
+            assert jit.get_pin_state(p) == eng.get_pin_state(p), (step, p)
