@@ -309,7 +309,11 @@ def run_ours(a):
                 "traffic": traffic, "kernel": "k_eval_level", "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes_step / level_launches,
                 "avg_launch_us": avg_launch_s * 1e6, "launches_per_step": level_launches,
-                "eval_share_of_step": eval_total / ms}
+                "eval_share_of_step": eval_total / ms,
+                "note": "achieved counts ALGORITHMIC bytes (24 B per gate-word, SURVEY 8d); with %d-word tiles "
+                        "part of them is served by L2 (previous level's rows, recycled scratch slots), so frac "
+                        "can exceed 1 while real DRAM traffic stays below the peak - see traffic and "
+                        "profiles/r01_ncu_eval_level.md" % eng.tile_words}
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ----------------------
     e2e = None
