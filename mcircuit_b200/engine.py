@@ -395,6 +395,8 @@ class B200Engine(Executor):
         if np.isscalar(value) or isinstance(value, int):
             self._poke_signals(base, width, int(value) & ((1 << width) - 1))
             return
+        if hasattr(value, "detach"):                            # a torch tensor, on any device
+            value = value.detach().cpu().numpy()
         v = np.ascontiguousarray(np.asarray(value).astype(np.uint64, copy=False))
         if v.shape != (self.lanes,):
             raise ValueError("expected %d lane values, got shape %s" % (self.lanes, v.shape))
@@ -616,6 +618,29 @@ class B200Engine(Executor):
 
     def pin_widths(self, pins: Sequence[str]) -> List[int]:
         return [self._slots_of(p)[1] for p in pins]
+
+    # ---- checkpoint / resume -------------------------------------------------------------------------
+    def state_dict(self):
+        """Everything that survives a step: the persistent plane (all lanes) and the step count.
+        Scratch rows are dead between steps, so they are not saved."""
+        P = self.program.n_persist
+        rows = self.rt.to_host_u64(self._plane[:P * self.stride]).reshape(P, self.stride)[:, :self.words]
+        return {"persist": np.ascontiguousarray(rows), "steps_done": self.steps_done, "lanes": self.lanes,
+                "n_persist": P, "records_crc": int(np.bitwise_xor.reduce(self.program.records.view(np.uint32).ravel()
+                                                                         .astype(np.uint64))) if self.program.n_ops else 0}
+
+    def load_state_dict(self, state):
+        P = self.program.n_persist
+        if state["lanes"] != self.lanes or state["n_persist"] != P:
+            raise ValueError("checkpoint is for another engine geometry")
+        crc = int(np.bitwise_xor.reduce(self.program.records.view(np.uint32).ravel().astype(np.uint64))) \
+            if self.program.n_ops else 0
+        if state.get("records_crc", crc) != crc:
+            raise ValueError("checkpoint is for another netlist")
+        full = np.zeros((P, self.stride), dtype=np.uint64)
+        full[:, :self.words] = state["persist"]
+        self._plane[:P * self.stride] = self.rt.to_device(full.reshape(-1))
+        self.steps_done = int(state["steps_done"])
 
     # ---- accounting ----------------------------------------------------------------------------------------
     def synchronize(self):

@@ -1,3 +1,3 @@
 mkdir -p gpurun_out
-timeout 600 python bench.py --verify > gpurun_out/bench_full.log 2>&1; echo "rc=$?" >> gpurun_out/bench_full.log
-tail -c 700 gpurun_out/bench_full.log
+timeout 100 python bench.py --no-cpu-baseline --no-e2e --steps 2 --warmup 3 > gpurun_out/bench_sanity.log 2>&1; echo "rc=$?" >> gpurun_out/bench_sanity.log
+tail -c 600 gpurun_out/bench_sanity.log

@@ -137,3 +137,23 @@ def test_netlist_file_loads_into_the_reference_too(reference, tmp_path):
         eng.step()
         for p in probes:
             assert jit.get_pin_state(p) == eng.get_pin_state(p), (step, p)
+
+
+def test_checkpoint_resume():
+    """state_dict / load_state_dict: a run resumed from a checkpoint continues bit-exactly."""
+    root = circuits.lfsr_pipeline(MD, 3, 8, 6, taps=(7, 5, 1, 0))
+    a = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode="resident", keep="ports")
+    for n in range(3):
+        a.set_pin_state(f"/l{n}_q0/out", 1)
+    a.run(11)
+    snap = a.state_dict()
+    a.run(20)
+    b = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode="levels", keep="ports")
+    b.load_state_dict(snap)
+    assert b.steps_done == 11
+    b.run(20)
+    for p in a.output_pins():
+        assert np.array_equal(a.get_pin_planes(p), b.get_pin_planes(p)), p
+    other = B200Engine(circuits.counter_circuit(MD), 1, True, lanes=128, runtime=CpuRuntime())
+    with pytest.raises(ValueError):
+        other.load_state_dict(snap)
