@@ -10,8 +10,9 @@
  * Conventions
  *   - plain C types only; every `d_` pointer is a DEVICE pointer owned by the caller (the
  *     Python host keeps them alive as torch tensors); `h_` pointers are host memory;
- *   - the library allocates no persistent device memory; `mcb_plan` is a host-side handle
- *     (a CUDA graph) that only remembers the pointers it was given;
+ *   - the library allocates no persistent device memory; the only host-side state it keeps
+ *     is the cache of instantiated CUDA graphs of `mcb_run` mode 1, which remember the
+ *     pointers they were captured with (`mcb_graph_cache_clear_owner`);
  *   - every call returns 0 on success or a negative code; `mcb_last_error()` returns the
  *     message of the calling thread's last failure; no C++ exception crosses the boundary;
  *   - all calls are asynchronous enqueues on `stream` (a `cudaStream_t` passed as `void*`,
@@ -95,6 +96,19 @@ int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void 
 int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
             const mcb_state *st, int64_t steps, int mode, void *stream);
 
+/* K3 v2 - serial run.  Replaces `step()` / `burst()` (core/simulator.py:195-245, :293-297) in
+ * the reference's own execution model: every micro-op in emit order, in place, `steps` times,
+ * each thread on its own (slice of a) lane column, one launch, no barrier.  `d_records` is a
+ * serial stream (mcircuit_b200/serial.py): 16-byte records of four `slot(24) | meta(8) << 24`
+ * words, a multiple of 8 records; operands come from memory (loaded a block of 8 records
+ * ahead, or just in time when an earlier record of the block stores that slot), from the
+ * accumulator (the previous record's result) or from the guard register; a GUARD record lets
+ * a warp whose enable word is zero in every lane jump over the region it guards.
+ * `word_bytes`: bytes of a lane word one thread owns (0 = automatic; 8, 4, 2 or 1).
+ * `d_skipped`: optional device counter, += the guarded regions warp 0 jumped over.          */
+int mcb_run_serial(const uint32_t *d_records, int n_records, const mcb_state *st, int64_t steps,
+                   int word_bytes, uint64_t *d_skipped, void *stream);
+
 /* K1g - mcb_eval_levels on the GROUPED stream: per level the records are sorted by base opcode
  * and every opcode group is padded to a multiple of 4 records (padding reads and writes a
  * trash slot), so a thread decodes one opcode per batch and the batch body is branch-free.   */
@@ -106,11 +120,13 @@ int mcb_eval_levels_grouped(const uint32_t *d_records, const int32_t *h_level_of
  * grid barriers, on the grouped stream with operand streaming hints (bit 31 of in0 / in1 =
  * "producer is two or more levels back: stream it through L2"; slots are the low 31 bits).  `st->d_scratch` is the
  * scratch plane of in-flight slot 0, the others follow at `scratch_plane_words`; `d_sync`
- * is 64 bytes of caller-owned device memory (zeroed by the call).                           */
+ * is 64 bytes of caller-owned device memory (zeroed by the call): one 64-bit monotonic
+ * arrival counter per in-flight slot, so the barrier cannot wrap however many steps one
+ * launch runs.                                                                              */
 int mcb_run_pipelined(const uint32_t *d_records, const int32_t *d_level_off,
                       const int32_t *h_level_off, int n_levels, const mcb_state *st,
                       int64_t tile_words, int in_flight, int64_t scratch_plane_words,
-                      uint32_t *d_sync, int64_t steps, void *stream);
+                      uint64_t *d_sync, int64_t steps, void *stream);
 
 /* K4 - signatures and toggle counts (new capability; no reference counterpart - the
  * reference only peeks one pin at a time, core/simulator.py:285-287).  For each of `n`
@@ -151,13 +167,22 @@ int mcb_capture_rows(const int32_t *d_slots, int n, const mcb_state *st, uint64_
 int mcb_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,
                int64_t width_bytes, int64_t rows, int kind, void *stream);
 
-/* mcb_run mode 1 keeps one instantiated CUDA graph per (netlist, tile geometry, tuning); call
- * this before freeing the buffers they point into.  Returns the number of graphs dropped.   */
+/* mcb_run mode 1 keeps one instantiated CUDA graph per (netlist, tile geometry, tuning), at
+ * most 8,192 (least recently used quarter evicted beyond that).  An engine that is going away
+ * calls mcb_graph_cache_clear_owner(its d_records) before freeing the buffers its graphs point
+ * into - other engines' graphs stay; mcb_graph_cache_clear drops everything.  Both return the
+ * number of graphs dropped.  Graphs are launched under the cache lock, so a concurrent clear
+ * cannot destroy an exec that is about to be launched.                                      */
 int mcb_graph_cache_clear(void);
+int mcb_graph_cache_clear_owner(const uint32_t *d_records);
+int mcb_graph_cache_size(void);
 
 /* tuning knobs (block size, gates per block ...); returns the previous value              */
 int mcb_set_tuning(const char *key, int value);
-/* number of kernel launches this library has issued on this thread since the last reset   */
+/* every knob back to the shipped default                                                   */
+int mcb_reset_tuning(void);
+/* number of kernel launches (graph kernel nodes included) this library has issued in this
+ * PROCESS since the last reset - one atomic counter shared by all threads                  */
 int64_t mcb_launch_count(int reset);
 
 #ifdef __cplusplus

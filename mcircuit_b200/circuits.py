@@ -359,11 +359,13 @@ def lfsr_pipeline(M=_own, n_lfsr=256, lfsr_bits=32, stages=1000, taps=(31, 21, 1
 
 
 # ---- C5: random levelized DAG ---------------------------------------------------------------------------------
-def random_dag(M=_own, n_gates=1_000_000, depth=200, n_inputs=4096, seed=TOPOLOGY_SEED, width=1):
+def random_dag(M=_own, n_gates=1_000_000, depth=200, n_inputs=4096, seed=TOPOLOGY_SEED, width=1,
+               in1_window: Optional[int] = None):
     """``depth`` levels x ``n_gates // depth`` two-input gates.  op uniform in {AND, OR,
     XOR}, negated Bernoulli(1/2); in0 uniform from the previous level, in1 uniform from any
     earlier level or the primary inputs (long-lived values).  Outputs = the last level.
-    Ports: /i{k}/pin -> /o{k}/pin."""
+    Ports: /i{k}/pin -> /o{k}/pin.  ``in1_window=w`` (measurement only) draws in1 from the last
+    ``w`` levels instead, which keeps the live set small enough to stay in L2."""
     rng = random.Random(seed)
     per = n_gates // depth
     ein, eout = M.ExposedPin(M.ExposedPin.IN, width), M.ExposedPin(M.ExposedPin.OUT, width)
@@ -384,7 +386,7 @@ def random_dag(M=_own, n_gates=1_000_000, depth=200, n_inputs=4096, seed=TOPOLOG
         for k in range(per):
             g = names[lo + k]
             s0 = names[rng.randrange(prev_lo, prev_hi)]
-            s1 = names[rng.randrange(0, lo)]
+            s1 = names[rng.randrange(0 if in1_window is None else max(0, lo - in1_window * per), lo)]
             connect(s0, "out" if s0[0] == "g" else "", g, "in0")
             connect(s1, "out" if s1[0] == "g" else "", g, "in1")
         prev_lo, prev_hi = lo, lo + per

@@ -412,6 +412,7 @@ class _Ops:
         self.first_temp = n_signals
         self.allow3 = allow3
         self.dead = set()                 # pin signals orphaned by edge-detector sharing
+        self.net_sig = None               # this compile's net -> first signal map (a COPY of the design's)
 
     def temp(self) -> int:
         t = self.n_sig
@@ -564,11 +565,15 @@ def lower(design: Design, allow3: bool = True, share_edge_detectors: bool = Fals
     members' ``prevclock`` pins become views of the leader's bit.  Exact unless a member's
     ``prevclock`` is poked individually (a poke then reaches the whole group) - hence opt-in."""
     ops = _Ops(design.n_signals, allow3)
-    net_sig = design.net_sig
+    # sharing redirects the members' prevclock nets to the leader's bit: do that on a private
+    # copy, so compiling one Design twice (or with and without sharing) gives the same result
+    net_sig = ops.net_sig = design.net_sig.copy()
     pin_net = design.pin_net
     pin_width = design.pin_width
-    groups: Dict[Tuple[int, bool], Tuple[int, int]] = {}       # (clock signal, already written) -> (rise, prevclock)
-    written = set()
+    # (clock signal, number of writes to it so far this step) -> (rise, prevclock): members that
+    # read the clock net between different writes of it see different values and never share
+    groups: Dict[Tuple[int, int], Tuple[int, int]] = {}
+    written: Dict[int, int] = {}
     n_seen = 0
     pins_per_net = np.bincount(pin_net, minlength=len(design.net_width)) if share_edge_detectors else None
 
@@ -579,7 +584,7 @@ def lower(design: Design, allow3: bool = True, share_edge_detectors: bool = Fals
             return
         prev_pin = design.leaf_pin_base[leaf] + design.leaf_table[leaf].index["prevclock"]
         alone = pins_per_net[pin_net[prev_pin]] == 1            # nothing else wired to prevclock
-        key = (p["clock"][0], p["clock"][0] in written)
+        key = (p["clock"][0], written.get(p["clock"][0], 0))
         hit = groups.get(key) if alone else None
         if hit is not None:
             rise, leader_prev = hit
@@ -631,7 +636,8 @@ def lower(design: Design, allow3: bool = True, share_edge_detectors: bool = Fals
             _lower_adder(ops, desc, p["cin"], p["a"], p["b"], p["cout"], p["sum"])
         # ExposedPin, Constant and anything not in TRANSLATOR emit nothing (:214-221)
         if share_edge_detectors:
-            written.update(ops.out[n_seen:])
+            for o in ops.out[n_seen:]:
+                written[o] = written.get(o, 0) + 1
             n_seen = len(ops.out)
     return ops
 
@@ -657,6 +663,8 @@ class Program:
     constants: List[Tuple[int, int, int]]   # (first signal, width, value) poked after build
     max_level_gates: int = 0
     records_hinted: Optional[np.ndarray] = None   # records + streaming hints (bit 31 of in0/in1)
+    net_sig: Optional[np.ndarray] = None          # net -> first signal of THIS compile (edge-detector sharing redirects some)
+    serial: bool = False                          # records are a serial stream (compile_serial), not levels
 
     @property
     def n_slots(self) -> int:
@@ -666,7 +674,8 @@ class Program:
     def pin_signals(self, path: str) -> Tuple[int, int]:
         pin = self.design.find_pin(path)
         net = int(self.design.pin_net[pin])
-        return int(self.design.net_sig[net]), self.design.pin_width[pin]
+        net_sig = self.net_sig if self.net_sig is not None else self.design.net_sig
+        return int(net_sig[net]), self.design.pin_width[pin]
 
     def pin_slots(self, path: str, need_value: bool = True) -> List[int]:
         base, width = self.pin_signals(path)
@@ -821,7 +830,7 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
         for path in observe:
             want.append(design.find_pin(path))
         for pin in want:
-            base = int(design.net_sig[design.pin_net[pin]])
+            base = int(ops.net_sig[design.pin_net[pin]])
             for s in range(base, base + design.pin_width[pin]):
                 persistent[s] = 1
                 kept[s] = True
@@ -955,10 +964,11 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
     for leaf, desc in enumerate(design.leaf_desc):
         if _type_name(desc) == "Constant":
             pin = design.leaf_pin_base[leaf] + design.leaf_table[leaf].index["out"]
-            base = int(design.net_sig[design.pin_net[pin]])
+            base = int(ops.net_sig[design.pin_net[pin]])
             constants.append((base, design.pin_width[pin], int(desc.value)))
 
     return Program(
+        net_sig=ops.net_sig,
         design=design, records=records, level_off=level_off.astype(np.int32),
         n_levels=n_levels, has_latch=has_latch, n_persist=n_persist, n_scratch=n_scratch,
         sig_slot=sig_slot, sig_shadow={s: int(sig_slot[sh]) for s, sh in shadow_sig.items()},

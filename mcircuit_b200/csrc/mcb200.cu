@@ -16,6 +16,8 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <vector>
+#include <algorithm>
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -70,17 +72,36 @@ struct Tuning {
     int persist_hints = 1;      // honour the operand streaming hints (bit 31)
     int persist_ctas_per_sm = 1;  // 0: as many as fit
     int persist_block = 1024;   // threads per CTA of the persistent level kernel
+    int serial_block = 128;     // threads per CTA of the serial kernel (warps are independent)
+    int serial_word_bytes = 0;  // bytes of a lane column per thread (0: auto, 8, 4, 2, 1)
 };
 static Tuning g_tune;
 static int g_sm_count = 0;
 
 // cached step graphs of mcb_run mode 1 (host-side handles only; they remember pointers)
-struct GraphEntry { cudaGraphExec_t exec; long long nodes; };
+// A key starts with the record-stream pointer, which is what identifies the owning engine
+// (mcb_graph_cache_clear_owner).  Entries are launched UNDER the mutex, so an engine that is
+// being dropped on another thread cannot destroy an exec between lookup and launch.
+struct GraphEntry { cudaGraphExec_t exec; long long nodes; unsigned long long last_use; };
 static std::mutex g_graph_mu;
 static std::unordered_map<std::string, GraphEntry> g_graphs;
+static unsigned long long g_graph_tick = 0;
+static const size_t GRAPH_CACHE_CAP = 8192;
 static void clear_graphs_locked() {
     for (auto &kv : g_graphs) cudaGraphExecDestroy(kv.second.exec);
     g_graphs.clear();
+}
+static void evict_graphs_locked() {
+    // drop the least recently used quarter (never everything: live engines keep their graphs)
+    std::vector<unsigned long long> ticks;
+    ticks.reserve(g_graphs.size());
+    for (auto &kv : g_graphs) ticks.push_back(kv.second.last_use);
+    std::nth_element(ticks.begin(), ticks.begin() + ticks.size() / 4, ticks.end());
+    const unsigned long long cut = ticks[ticks.size() / 4];
+    for (auto it = g_graphs.begin(); it != g_graphs.end();) {
+        if (it->second.last_use <= cut) { cudaGraphExecDestroy(it->second.exec); it = g_graphs.erase(it); }
+        else ++it;
+    }
 }
 
 static int sm_count() {
@@ -406,7 +427,7 @@ struct PipeArgs {
     int n_tiles;
     int n_levels;
     long long steps;
-    unsigned int *sync;         // G monotonic arrival counters, zeroed by the host
+    unsigned long long *sync;   // G monotonic 64-bit arrival counters, zeroed by the host (never wrap)
 };
 
 template <int U, int G, int HINTS>
@@ -414,7 +435,8 @@ __global__ void __launch_bounds__(1024, 1)
 k_eval_pipelined(const uint4 *__restrict__ recs, const int *__restrict__ level_off, PipeArgs a) {
     const uint64_t pol_stream = make_policy_evict_first();
     const uint64_t pol_keep = make_policy_evict_last();
-    unsigned int arrivals[G];
+    // 64-bit on purpose: arrivals x n_cta passes 2^32 after a few hundred steps of a C5-sized run
+    unsigned long long arrivals[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) arrivals[g] = 0;
     const unsigned int n_cta = gridDim.x;
@@ -440,8 +462,8 @@ k_eval_pipelined(const uint4 *__restrict__ recs, const int *__restrict__ level_o
                     v.n_words = ncols;
                     // wait: every CTA has finished this slot's previous phase
                     if (threadIdx.x == 0) {
-                        const unsigned int target = arrivals[g] * n_cta;
-                        volatile unsigned int *c = a.sync + g;
+                        const unsigned long long target = arrivals[g] * (unsigned long long)n_cta;
+                        volatile unsigned long long *c = a.sync + g;
                         while (*c < target) { }
                         __threadfence();
                     }
@@ -459,7 +481,7 @@ k_eval_pipelined(const uint4 *__restrict__ recs, const int *__restrict__ level_o
                     __syncthreads();
                     if (threadIdx.x == 0) {
                         __threadfence();
-                        atomicAdd(a.sync + g, 1u);
+                        atomicAdd(a.sync + g, 1ull);
                     }
                     arrivals[g] += 1;
                 }
@@ -806,6 +828,105 @@ static int launch_resident(const uint4 *recs, int n_recs, const View &v, long lo
 }
 
 // ------------------------------------------------------------------------------------------
+// K3 v2: serial run.  A thread owns (a slice of) one lane column and executes the reference's
+// step() exactly as the reference does - every micro-op in emit order, in place - for `steps`
+// steps, with no barrier of any kind (lanes never interact; warps are fully independent).
+// See mcircuit_b200/serial.py for the record format.  Per block of 8 records:
+//   phase 1: the 8 records (one 128-byte line, same address in every thread: a broadcast), every
+//            EARLY operand load of the block, and the L2 prefetches the records carry;
+//   phase 2: the records in order - LATE loads, accumulator / guard-register operands, the
+//            bitwise op, the store (elided when the next record is the only reader).
+// A GUARD record (always the last of its block) loads the region's enable word; when it is zero
+// in every lane of the warp, the warp jumps over the region: MUX(0, d, out) -> out and out ^= 0
+// are the identity, so skipping is exact (event-driven evaluation of idle clock phases).
+// ------------------------------------------------------------------------------------------
+#define SER_BLOCK 8
+#define SER_M24 0x00ffffffu
+enum { SK_NONE = 0, SK_EARLY = 1, SK_LATE = 2, SK_ACC = 3, SK_GREG = 4 };
+#define MCB_OP_GUARD 11
+
+template <typename W, bool UNIFIED>
+__global__ void __launch_bounds__(128)
+k_run_serial(const uint4 *__restrict__ recs, int n_recs, View v, long long steps, long long n_cols,
+             unsigned long long *__restrict__ skipped) {
+    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = col < n_cols;
+    const unsigned warp_mask = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const GlobalCols<W, UNIFIED> cols(v, col);
+    W acc = 0, greg = 0;
+    unsigned long long n_skipped = 0;
+    for (long long step = 0; step < steps; ++step) {
+        int ip = 0;
+        while (ip < n_recs) {
+            uint4 r[SER_BLOCK];
+            W va[SER_BLOCK], vb[SER_BLOCK], vc[SER_BLOCK];
+#pragma unroll
+            for (int u = 0; u < SER_BLOCK; ++u) r[u] = __ldg(recs + ip + u);
+#pragma unroll
+            for (int u = 0; u < SER_BLOCK; ++u) {
+                const uint32_t ka = (r[u].y >> 24) & 7u, kb = (r[u].y >> 27) & 7u, kc = (r[u].z >> 24) & 7u;
+                const uint32_t pf = r[u].y >> 30;
+                va[u] = vb[u] = vc[u] = 0;
+                if (ka == SK_EARLY) va[u] = cols.ld(r[u].x & SER_M24);
+                if (kb == SK_EARLY) vb[u] = cols.ld(r[u].y & SER_M24);
+                if (kc == SK_EARLY) vc[u] = cols.ld(r[u].z & SER_M24);
+                if (pf) {
+                    const uint32_t slot = (pf == 1 ? r[u].x : (pf == 2 ? r[u].y : r[u].z)) & SER_M24;
+                    asm volatile("prefetch.global.L2 [%0];" :: "l"(cols.at(slot)));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < SER_BLOCK; ++u) {
+                const uint32_t flags = r[u].x >> 24;
+                const uint32_t op = flags & 15u;
+                if (op == MCB_OP_NOP || op == MCB_OP_GUARD) continue;       // warp-uniform
+                const uint32_t ka = (r[u].y >> 24) & 7u, kb = (r[u].y >> 27) & 7u, kc = (r[u].z >> 24) & 7u;
+                W a = va[u], b = vb[u], c = vc[u];
+                if (ka >= SK_LATE) a = (ka == SK_ACC) ? acc : (ka == SK_GREG ? greg : cols.ld(r[u].x & SER_M24));
+                if (kb >= SK_LATE) b = (kb == SK_ACC) ? acc : (kb == SK_GREG ? greg : cols.ld(r[u].y & SER_M24));
+                if (kc >= SK_LATE) c = (kc == SK_ACC) ? acc : (kc == SK_GREG ? greg : cols.ld(r[u].z & SER_M24));
+                W res = apply_op_w<W>(op | ((flags & 16u) << 3), a, b, c);
+                if (flags & 32u) cols.st(r[u].w & SER_M24, res);
+                if (!(flags & 64u)) acc = res;
+            }
+            // a guard is always the last record of its block
+            if (((r[SER_BLOCK - 1].x >> 24) & 15u) == MCB_OP_GUARD) {
+                greg = cols.ld(r[SER_BLOCK - 1].x & SER_M24);
+                if (__all_sync(warp_mask, greg == 0)) {
+                    ip += (int)(r[SER_BLOCK - 1].w & SER_M24);
+                    n_skipped += 1;
+                }
+            }
+            ip += SER_BLOCK;
+        }
+    }
+    if (skipped && n_skipped && (threadIdx.x & 31) == __ffs(warp_mask) - 1 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0)
+        atomicAdd(skipped, n_skipped);
+}
+
+template <typename W>
+static int launch_serial_w(const uint4 *recs, int n_recs, const View &v, long long steps,
+                           unsigned long long *d_skipped, cudaStream_t s) {
+    const long long cols = v.n_words * (long long)(8 / sizeof(W));
+    int block = g_tune.serial_block;
+    if (block > 128) block = 128;
+    if (block < 32) block = 32;
+    block = block / 32 * 32;
+    // warps are independent: spread them over the SMs first, then stack them
+    while (block > 32 && (cols + block - 1) / block < (long long)sm_count() * 2) block /= 2;
+    const long long grid = (cols + block - 1) / block;
+    if (v.pstride * 8 >= (1ll << 32) || v.sstride * 8 >= (1ll << 32))
+        return fail(MCB_ERR_ARG, "row stride of 4 GB or more is not supported by the serial kernel");
+    const bool unified = v.scratch_biased == nullptr ||
+                         (v.scratch_biased == v.persist && v.sstride == v.pstride);
+    if (unified) k_run_serial<W, true><<<(unsigned)grid, block, 0, s>>>(recs, n_recs, v, steps, cols, d_skipped);
+    else k_run_serial<W, false><<<(unsigned)grid, block, 0, s>>>(recs, n_recs, v, steps, cols, d_skipped);
+    LAUNCH_CHECK("k_run_serial");
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // K4: signatures / toggles.  One CTA per slot; lane words are folded with popc, the 64-bit
 // partial sums cross lanes by warp shuffle and cross warps through shared memory.
 // ------------------------------------------------------------------------------------------
@@ -979,10 +1100,17 @@ int mcb_set_tuning(const char *key, int value) {
     else if (!strcmp(key, "persist_hints")) p = &g_tune.persist_hints;
     else if (!strcmp(key, "persist_ctas_per_sm")) p = &g_tune.persist_ctas_per_sm;
     else if (!strcmp(key, "persist_block")) p = &g_tune.persist_block;
+    else if (!strcmp(key, "serial_block")) p = &g_tune.serial_block;
+    else if (!strcmp(key, "serial_word_bytes")) p = &g_tune.serial_word_bytes;
     else return fail(MCB_ERR_ARG, "unknown tuning key %s", key);
     int old = *p;
     *p = value;
     return old;
+}
+
+int mcb_reset_tuning(void) {
+    g_tune = Tuning();
+    return 0;
 }
 
 int mcb_device_info(int device, int *sms, int *cc_major, int *cc_minor, int64_t *total_mem,
@@ -1081,36 +1209,63 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
         key.append((const char *)&dev, sizeof(dev));
         key.push_back(hinted ? 'h' : 'p');
     }
-    cudaGraphExec_t exec = nullptr;
-    long long per_step = 0;
-    {
-        std::lock_guard<std::mutex> lock(g_graph_mu);
-        auto it = g_graphs.find(key);
-        if (it != g_graphs.end()) { exec = it->second.exec; per_step = it->second.nodes; }
-    }
-    if (!exec) {
+    // capture (first use) and every launch happen under the cache mutex
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    auto it = g_graphs.find(key);
+    if (it == g_graphs.end()) {
         cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
         const long long before = g_launches.load();
         CUDA_TRY(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         rc = eval_levels_impl(d_records, h_level_off, 0, n_levels, st, stream, hinted);
         cudaError_t ce = cudaStreamEndCapture(s, &graph);
-        per_step = g_launches.load() - before;             // nodes captured, nothing ran yet
+        const long long per_step = g_launches.load() - before;   // nodes captured, nothing ran yet
         g_launches.store(before);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (ce != cudaSuccess) return fail(MCB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(ce));
         ce = cudaGraphInstantiate(&exec, graph, 0);
         cudaGraphDestroy(graph);
         if (ce != cudaSuccess) return fail(MCB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(ce));
-        std::lock_guard<std::mutex> lock(g_graph_mu);
-        if (g_graphs.size() >= 4096) clear_graphs_locked();
-        g_graphs[key] = GraphEntry{exec, per_step};
+        if (g_graphs.size() >= GRAPH_CACHE_CAP) evict_graphs_locked();
+        it = g_graphs.emplace(key, GraphEntry{exec, per_step, 0}).first;
     }
+    it->second.last_use = ++g_graph_tick;
     for (int64_t t = 0; t < steps; ++t) {
-        cudaError_t le = cudaGraphLaunch(exec, s);
+        cudaError_t le = cudaGraphLaunch(it->second.exec, s);
         if (le != cudaSuccess) return fail(MCB_ERR_CUDA, "graph launch failed: %s", cudaGetErrorString(le));
-        g_launches.fetch_add(per_step, std::memory_order_relaxed);
+        g_launches.fetch_add(it->second.nodes, std::memory_order_relaxed);
     }
     return 0;
+}
+
+int mcb_run_serial(const uint32_t *d_records, int n_records, const mcb_state *st, int64_t steps,
+                   int word_bytes, uint64_t *d_skipped, void *stream) {
+    int rc = check_state(st);
+    if (rc) return rc;
+    if (n_records < 0 || (n_records > 0 && !d_records) || steps < 0)
+        return fail(MCB_ERR_ARG, "bad serial-run arguments");
+    if (n_records % SER_BLOCK) return fail(MCB_ERR_ARG, "serial stream must be a multiple of %d records", SER_BLOCK);
+    if (n_records == 0 || steps == 0 || st->n_words == 0) return 0;
+    if (st->n_slots > (1 << 24)) return fail(MCB_ERR_ARG, "serial records address at most 2^24 slots");
+    const View v = make_view(st);
+    const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long *sk = reinterpret_cast<unsigned long long *>(d_skipped);
+    if (word_bytes == 0) word_bytes = g_tune.serial_word_bytes;
+    if (word_bytes == 0) {
+        // narrower words = more independent warps (latency hiding) but more instructions per byte:
+        // split until every SM has about 8 warps
+        const long long want = (long long)sm_count() * 256;
+        word_bytes = 8;
+        while (word_bytes > 2 && st->n_words * (8 / word_bytes) < want) word_bytes /= 2;
+    }
+    switch (word_bytes) {
+        case 8: return launch_serial_w<uint64_t>(recs, n_records, v, steps, sk, s);
+        case 4: return launch_serial_w<uint32_t>(recs, n_records, v, steps, sk, s);
+        case 2: return launch_serial_w<uint16_t>(recs, n_records, v, steps, sk, s);
+        case 1: return launch_serial_w<uint8_t>(recs, n_records, v, steps, sk, s);
+        default: return fail(MCB_ERR_ARG, "word_bytes must be 1, 2, 4 or 8");
+    }
 }
 
 int mcb_graph_cache_clear(void) {
@@ -1120,10 +1275,27 @@ int mcb_graph_cache_clear(void) {
     return n;
 }
 
+int mcb_graph_cache_clear_owner(const uint32_t *d_records) {
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    int n = 0;
+    for (auto it = g_graphs.begin(); it != g_graphs.end();) {
+        const void *owner = nullptr;
+        memcpy(&owner, it->first.data(), sizeof(owner));
+        if (owner == (const void *)d_records) { cudaGraphExecDestroy(it->second.exec); it = g_graphs.erase(it); ++n; }
+        else ++it;
+    }
+    return n;
+}
+
+int mcb_graph_cache_size(void) {
+    std::lock_guard<std::mutex> lock(g_graph_mu);
+    return (int)g_graphs.size();
+}
+
 int mcb_run_pipelined(const uint32_t *d_records, const int32_t *d_level_off,
                       const int32_t *h_level_off, int n_levels, const mcb_state *st,
                       int64_t tile_words, int in_flight, int64_t scratch_plane_words,
-                      uint32_t *d_sync, int64_t steps, void *stream) {
+                      uint64_t *d_sync, int64_t steps, void *stream) {
     if (!st) return fail(MCB_ERR_ARG, "state is NULL");
     mcb_state one = *st;                     // geometry of one tile for the stride checks
     if (one.n_words > tile_words) one.n_words = tile_words;
@@ -1150,7 +1322,7 @@ int mcb_run_pipelined(const uint32_t *d_records, const int32_t *d_level_off,
     a.n_tiles = (int)((st->n_words + tile_words - 1) / tile_words);
     a.n_levels = n_levels;
     a.steps = steps;
-    a.sync = d_sync;
+    a.sync = reinterpret_cast<unsigned long long *>(d_sync);
     if (a.n_tiles > 1 && (st->n_slots > st->n_persist) && scratch_plane_words <= 0)
         return fail(MCB_ERR_ARG, "scratch_plane_words must be given when several tiles are in flight");
     const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);

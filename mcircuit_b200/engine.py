@@ -57,7 +57,8 @@ class B200Engine(Executor):
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
                  resident_word_bytes=0, in_flight=2, streams=None, level_hints=False,
-                 share_edge_detectors=False, sort_level_by_fanin=False):
+                 share_edge_detectors=False, sort_level_by_fanin=False, serial_guard=True,
+                 serial_prefetch=64, serial_word_bytes=0):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -78,16 +79,26 @@ class B200Engine(Executor):
             design = compiler.flatten(root, map_pins)
             if keep == "auto":
                 keep = "all" if (design.n_signals * 3 // 2) * self.stride * 8 <= budget // 2 else "ports"
-            program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges,
-                                              share_edge_detectors=share_edge_detectors,
-                                              sort_level_by_fanin=sort_level_by_fanin)
+            if mode == "serial":
+                from . import serial
+                program = serial.compile_serial(design, keep=keep, observe=observe,
+                                                share_edge_detectors=share_edge_detectors,
+                                                guard=serial_guard, prefetch_distance=serial_prefetch)
+            else:
+                program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges,
+                                                  share_edge_detectors=share_edge_detectors,
+                                                  sort_level_by_fanin=sort_level_by_fanin)
+        if getattr(program, "serial", False):
+            if mode not in ("auto", "serial"):
+                raise ValueError("a serial program runs in mode='serial' only")
+            mode = "serial"
+        elif mode == "serial":
+            raise ValueError("mode='serial' needs a program made by serial.compile_serial")
         self.program = program
         self.keep = keep
         # one extra scratch row that padding records of the resident kernel read and write
         P, S = program.n_persist, program.n_scratch + 1
         self.trash_slot = P + S - 1
-        if self.trash_slot >= compiler.IN2_LIMIT:
-            raise compiler.CircuitError("too many slots for the resident kernel's padding records")
 
         self.in_flight = max(1, min(4, int(in_flight)))     # tiles in flight of the pipelined kernel
         # level mode: independent tiles alternate over this many CUDA streams (each with its own
@@ -128,9 +139,16 @@ class B200Engine(Executor):
             # per-level launches pay off only when one level of one tile keeps the whole GPU
             # busy for longer than a launch gap; otherwise one resident launch walks everything
             mode = "levels" if avg_level * self.tile_words >= (1 << 19) else "resident"
-        if mode not in ("levels", "levels_grouped", "resident", "persistent"):
-            raise ValueError("mode must be 'auto', 'levels', 'levels_grouped', 'resident' or 'persistent'")
+        if mode not in ("levels", "levels_grouped", "resident", "persistent", "serial"):
+            raise ValueError("mode must be 'auto', 'levels', 'levels_grouped', 'resident', 'serial' or 'persistent'")
         self.mode = mode
+        # padding records of the resident / grouped / pipelined streams carry the trash slot as
+        # in2, next to the opcode; plain level launches have no padding and no such limit
+        self.serial_word_bytes = int(serial_word_bytes)
+        self._skipped = None        # device counter of guarded regions warp 0 jumped over (serial mode)
+        if mode not in ("levels", "serial") and self.trash_slot >= compiler.IN2_LIMIT:
+            raise compiler.CircuitError("too many slots (%d) for the %s kernel's padding records; use mode='levels'"
+                                        % (self.trash_slot, mode))
 
         # ---- buffers (torch owns them) ---------------------------------------------------------------
         if self.n_tiles == 1:
@@ -148,7 +166,7 @@ class B200Engine(Executor):
         self._d_records = self.rt.to_device(program.records_hinted if self.level_hints else program.records)
         self._h_level_off = np.ascontiguousarray(program.level_off, dtype=np.int32)
         self._resident = None      # (d_records in batches, h_level_off), built on first use
-        # resident kernel: records per batch (4, 8, 16) and bytes of a lane word per thread (0 = auto)
+        # resident kernel: records per batch (4 or 8) and bytes of a lane word per thread (0 = auto)
         self.resident_batch = int(resident_batch) if resident_batch else 8
         self.resident_word_bytes = int(resident_word_bytes)
         self.resident_batches = None
@@ -161,10 +179,12 @@ class B200Engine(Executor):
             self._poke_signals(base, width, int(value))
 
     def close(self):
-        """Drop the cached step graphs (they hold raw pointers into this engine's buffers)."""
+        """Drop THIS engine's cached step graphs (they hold raw pointers into its buffers);
+        other engines' graphs stay."""
         clear = getattr(self.rt, "graph_cache_clear", None)
-        if clear is not None:
-            clear()
+        recs = getattr(self, "_d_records", None)
+        if clear is not None and recs is not None and hasattr(recs, "data_ptr"):
+            clear(recs)
 
     def __del__(self):
         try:
@@ -274,7 +294,12 @@ class B200Engine(Executor):
 
     def _run_tile(self, c0, n, steps, plane=0):
         """All ``steps`` passes of one lane tile (tiles are independent: lanes never interact)."""
-        if self.mode == "levels_grouped":
+        if self.mode == "serial":
+            if self._skipped is None:
+                self._skipped = self.rt.zeros_words(1)
+            self.rt.run_serial(self._d_records, len(self.program.records), self._state_for(c0, n), steps,
+                               self.serial_word_bytes, self._skipped)
+        elif self.mode == "levels_grouped":
             d_rec, _, h_off = self._grouped()
             st = self._state_for(c0, n, plane=plane)
             for _ in range(int(steps)):
@@ -641,6 +666,11 @@ class B200Engine(Executor):
         full[:, :self.words] = state["persist"]
         self._plane[:P * self.stride] = self.rt.to_device(full.reshape(-1))
         self.steps_done = int(state["steps_done"])
+
+    def regions_skipped(self) -> int:
+        """Serial mode: how many guarded regions the first warp jumped over so far (a sample of
+        what every warp does when all lanes share the clock)."""
+        return int(self.rt.to_host_u64(self._skipped)[0]) if self._skipped is not None else 0
 
     # ---- accounting ----------------------------------------------------------------------------------------
     def synchronize(self):

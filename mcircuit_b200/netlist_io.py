@@ -119,9 +119,10 @@ def save_program(program, path):
     slot table of every retained pin, enough to run and to address pins by path."""
     d = program.design
     paths, bases, widths = [], [], []
+    net_sig = program.net_sig if getattr(program, "net_sig", None) is not None else d.net_sig
     for pin in range(len(d.pin_width)):
         net = int(d.pin_net[pin])
-        base = int(d.net_sig[net])
+        base = int(net_sig[net])
         w = d.pin_width[pin]
         if bool(program.sig_kept[base:base + w].all()):
             paths.append(d.pin_path(pin))

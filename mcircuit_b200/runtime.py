@@ -46,6 +46,7 @@ _PROTOTYPES = [
     ("mcb_eval_levels", c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(McbState), c_void_p]),
     ("mcb_latch", c_int, [c_void_p, c_int, POINTER(McbState), c_void_p]),
     ("mcb_run", c_int, [c_void_p, c_void_p, c_int, POINTER(McbState), c_int64, c_int, c_void_p]),
+    ("mcb_run_serial", c_int, [c_void_p, c_int, POINTER(McbState), c_int64, c_int, c_void_p, c_void_p]),
     ("mcb_eval_levels_grouped", c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(McbState), c_void_p]),
     ("mcb_run_pipelined", c_int, [c_void_p, c_void_p, c_void_p, c_int, POINTER(McbState), c_int64, c_int,
                                   c_int64, c_void_p, c_int64, c_void_p]),
@@ -61,6 +62,9 @@ _PROTOTYPES = [
     ("mcb_capture_rows", c_int, [c_void_p, c_int, POINTER(McbState), c_void_p, c_int64, c_void_p]),
     ("mcb_copy2d", c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
     ("mcb_graph_cache_clear", c_int, []),
+    ("mcb_graph_cache_clear_owner", c_int, [c_void_p]),
+    ("mcb_graph_cache_size", c_int, []),
+    ("mcb_reset_tuning", c_int, []),
     ("mcb_set_tuning", c_int, [c_char_p, c_int]),
     ("mcb_launch_count", c_int64, [c_int]),
 ]
@@ -181,6 +185,12 @@ class CudaRuntime:
                 d_records.data_ptr(), h_level_off.ctypes.data, int(n_levels), ctypes.byref(st),
                 int(steps), int(mode), self._stream()))
 
+    def run_serial(self, d_records, n_records, st: McbState, steps, word_bytes=0, d_skipped=None):
+        with self.torch.cuda.device(self.device):
+            self._check(self.lib.mcb_run_serial(
+                d_records.data_ptr(), int(n_records), ctypes.byref(st), int(steps), int(word_bytes),
+                d_skipped.data_ptr() if d_skipped is not None else None, self._stream()))
+
     def eval_levels_grouped(self, d_records, h_level_off: np.ndarray, lo, hi, st: McbState):
         with self.torch.cuda.device(self.device):
             self._check(self.lib.mcb_eval_levels_grouped(
@@ -245,8 +255,17 @@ class CudaRuntime:
     def set_tuning(self, key: str, value: int) -> int:
         return self.lib.mcb_set_tuning(key.encode(), int(value))
 
-    def graph_cache_clear(self) -> int:
-        return int(self.lib.mcb_graph_cache_clear())
+    def graph_cache_clear(self, owner=None) -> int:
+        """Drop the cached step graphs of one engine (``owner`` = its record tensor) or all."""
+        if owner is None:
+            return int(self.lib.mcb_graph_cache_clear())
+        return int(self.lib.mcb_graph_cache_clear_owner(owner.data_ptr()))
+
+    def graph_cache_size(self) -> int:
+        return int(self.lib.mcb_graph_cache_size())
+
+    def reset_tuning(self):
+        self.lib.mcb_reset_tuning()
 
     def launch_count(self, reset=False) -> int:
         return int(self.lib.mcb_launch_count(1 if reset else 0))

@@ -157,6 +157,62 @@ class CpuRuntime:
             for _ in range(int(steps)):
                 self.eval_levels(d_records, h_level_off, 0, n_levels, st)
 
+    def run_serial(self, d_records, n_records, st, steps, word_bytes=0, d_skipped=None, warp_cols=32):
+        """The serial kernel's execution model, warp by warp (``warp_cols`` columns each): blocks
+        of 8 records, EARLY loads at block start, LATE loads in place, accumulator and guard
+        register, and a GUARD jump only when every lane of the warp has a zero enable."""
+        recs = np.asarray(d_records).astype(np.int64).reshape(-1, 4)[:n_records]
+        assert len(recs) % 8 == 0
+        M = 0xFFFFFF
+        self._launches += 1
+        for c0 in range(0, st.n_words, warp_cols):
+            n = min(warp_cols, st.n_words - c0)
+            sub = _State(st.persist, st.pstride, st.pcol + c0, st.scratch, st.sstride, st.scol + c0,
+                         st.n_persist, st.n_slots, n)
+            acc = np.zeros(n, dtype=U64)
+            greg = np.zeros(n, dtype=U64)
+            for _ in range(int(steps)):
+                ip = 0
+                while ip < len(recs):
+                    blk = recs[ip:ip + 8]
+                    early = {}
+                    for u, r in enumerate(blk):
+                        kinds = ((r[1] >> 24) & 7, (r[1] >> 27) & 7, (r[2] >> 24) & 7)
+                        for k in range(3):
+                            if kinds[k] == 1:
+                                early[(u, k)] = sub.read([r[k] & M])[0]
+                    for u, r in enumerate(blk):
+                        flags = r[0] >> 24
+                        op = flags & 15
+                        if op in (0, 11):
+                            continue
+                        kinds = ((r[1] >> 24) & 7, (r[1] >> 27) & 7, (r[2] >> 24) & 7)
+                        vals = []
+                        for k in range(3):
+                            if kinds[k] == 1:
+                                vals.append(early[(u, k)])
+                            elif kinds[k] == 2:
+                                vals.append(sub.read([r[k] & M])[0])
+                            elif kinds[k] == 3:
+                                vals.append(acc)
+                            elif kinds[k] == 4:
+                                vals.append(greg)
+                            else:
+                                vals.append(np.zeros(n, dtype=U64))
+                        res = _apply(int(op | (0x80 if flags & 16 else 0)), vals[0], vals[1], vals[2])
+                        if flags & 32:
+                            sub.write([r[3] & M], res[None, :])
+                        if not flags & 64:
+                            acc = res
+                    last = blk[7]
+                    if ((last[0] >> 24) & 15) == 11:
+                        greg = sub.read([last[0] & M])[0].copy()
+                        if not greg.any():
+                            ip += int(last[3] & M)
+                            if d_skipped is not None and c0 == 0:
+                                d_skipped[0] += U64(1)
+                    ip += 8
+
     def eval_levels_grouped(self, d_records, h_level_off, lo, hi, st):
         recs = d_records.astype(np.int64)
         recs[:, 1] &= 0x7FFFFFFF

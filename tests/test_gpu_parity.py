@@ -115,9 +115,9 @@ def test_gpu_vs_oracle_all_lanes(seed):
 @pytest.mark.parametrize("unroll", [1, 2, 4, 8])
 @pytest.mark.parametrize("cache", [0, 1])
 def test_gpu_level_kernel_variants(cuda_rt, unroll, cache):
+    old_unroll = cuda_rt.set_tuning("level_unroll", unroll)      # returns the previous value
+    old_cache = cuda_rt.set_tuning("level_cache", cache)
     try:
-        cuda_rt.set_tuning("level_unroll", unroll)
-        cuda_rt.set_tuning("level_cache", cache)
         case = golden("lane_trick.json")[3]
         ins, outs = lane_trick_planes(case)
         nw = case["n_words"]
@@ -128,8 +128,9 @@ def test_gpu_level_kernel_variants(cuda_rt, unroll, cache):
         for p, words in outs.items():
             assert np.array_equal(eng.get_pin_planes(p)[0], np.tile(words, 7)), p
     finally:
-        cuda_rt.set_tuning("level_unroll", 4)
-        cuda_rt.set_tuning("level_cache", 1)
+        # back to whatever was shipped (NOT a literal: the defaults live in mcb200.cu's Tuning)
+        cuda_rt.set_tuning("level_unroll", old_unroll)
+        cuda_rt.set_tuning("level_cache", old_cache)
 
 
 def test_gpu_pack_unpack_stimulus_signature():

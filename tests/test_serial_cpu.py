@@ -1,0 +1,181 @@
+"""not-gpu: serial programs (mcircuit_b200/serial.py) executed by the numpy test double, which
+follows the serial kernel's execution model (blocks of 8, EARLY / LATE loads, accumulator, guard
+register, per-warp region skipping), checked against the oracle and the golden vectors."""
+import numpy as np
+import pytest
+
+import mcircuit_b200.core.descriptors as MD
+from _cpu_runtime import CpuRuntime
+from _helpers import (build, compare_engine_to_oracle, golden, lane_trick_planes, run_register_case,
+                      run_trace_case)
+from mcircuit_b200 import circuits, compiler, serial
+from mcircuit_b200.engine import B200Engine
+
+TRACES = golden("traces.json")
+
+
+def serial_factory(keep="all", map_pins=True, **kw):
+    def make(root, burst_size, lanes=64):
+        return B200Engine(root, burst_size, map_pins, lanes=lanes, runtime=CpuRuntime(), mode="serial",
+                          keep=keep, **kw)
+    return make
+
+
+@pytest.mark.parametrize("case", TRACES, ids=[c["name"] for c in TRACES])
+@pytest.mark.parametrize("keep,map_pins,share", [("all", True, False), ("ports", True, True), ("all", False, False)])
+def test_serial_traces(case, keep, map_pins, share):
+    run_trace_case(case, serial_factory(keep, map_pins, share_edge_detectors=share),
+                   skip_unobservable=(keep == "ports"))
+
+
+@pytest.mark.parametrize("case", golden("register_intent.json"), ids=lambda c: c["name"])
+def test_serial_register_intent(case):
+    run_register_case(case, serial_factory())
+
+
+@pytest.mark.parametrize("case", golden("adder.json"), ids=lambda c: c["name"])
+def test_serial_adder(case):
+    w = case["width"]
+    top = MD.Composite()
+    top.add_child("add", MD.Adder(w))
+    vecs = case["vectors"]
+    lanes = (len(vecs) + 63) // 64 * 64
+    pad = lanes - len(vecs)
+    eng = serial_factory()(top, 1, lanes)
+    col = lambda k: np.array([v[k] for v in vecs] + [0] * pad, dtype=np.uint64)
+    eng.set_pin_state("/add/a", col(0))
+    eng.set_pin_state("/add/b", col(1))
+    eng.set_pin_state("/add/cin", col(2))
+    eng.step()
+    s = eng.get_pin_state("/add/sum", lanes=True)
+    c = eng.get_pin_state("/add/cout", lanes=True)
+    for i, (ws, wc) in enumerate(case["results"]):
+        assert (int(s[i]), int(c[i])) == (ws, wc), (w, vecs[i])
+
+
+@pytest.mark.parametrize("case", golden("lane_trick.json")[:5], ids=lambda c: c["name"])
+def test_serial_lane_trick(case):
+    ins, outs = lane_trick_planes(case)
+    nw = case["n_words"]
+    eng = B200Engine(build(case), 1, True, lanes=64 * nw * 3, runtime=CpuRuntime(), mode="serial", keep="ports")
+    for p, words in ins.items():
+        eng.set_pin_planes(p, np.tile(words, 3)[None, :])
+    eng.step()
+    for p, words in outs.items():
+        assert np.array_equal(eng.get_pin_planes(p)[0], np.tile(words, 3)), p
+
+
+@pytest.mark.parametrize("seed", range(100, 140))
+def test_serial_vs_oracle_all_lanes(seed):
+    prims = ("Gate", "Not", "Constant", "Clock", "Counter", "Counter", "Adder", "Register", "Register")
+    root, probes = circuits.random_circuit(MD, seed, n_nodes=26, primitives=prims)
+    d = compiler.flatten(root)
+    lane_inputs = [(p, d.pin_width[d.find_pin(p)]) for p in ("/in0/pin", "/in1/pin")]
+    compare_engine_to_oracle(lambda M: circuits.random_circuit(M, seed, n_nodes=26, primitives=prims),
+                             lambda r, bs, lanes: serial_factory(share_edge_detectors=bool(seed % 2))(r, bs, lanes),
+                             lanes=128, steps=8, probes=probes, lane_inputs=lane_inputs, seed=seed)
+
+
+@pytest.mark.parametrize("keep", ["all", "ports"])
+@pytest.mark.parametrize("share", [False, True])
+def test_serial_lfsr_pipeline_vs_oracle(keep, share):
+    """C4's shape: with shared edge detectors and keep='ports' nearly the whole step is one
+    guarded region, skipped on every non-rising step - results must not change."""
+    args = dict(n_lfsr=5, lfsr_bits=8, stages=40, taps=(7, 5, 1, 0))
+    probes = [f"/tap{n}/pin" for n in range(5)] + ["/pipe_out/pin", "/clk/out"]
+    if keep == "all":
+        probes += [f"/l1_q{b}/out" for b in range(8)] + [f"/p{k}/out" for k in (0, 7, 39)] + ["/px3/out"]
+    pokes = [(f"/l{n}_q{b}/out", (n + b) & 1) for n in range(5) for b in range(8)]
+    eng, _ = compare_engine_to_oracle(lambda M: circuits.lfsr_pipeline(M, **args),
+                                      lambda r, bs, lanes: serial_factory(keep, share_edge_detectors=share)(r, bs, lanes),
+                                      lanes=64 * 3, steps=24, probes=probes, pokes=pokes)
+    info = eng.program.serial_info
+    if share and keep == "ports":
+        assert info["regions"] == 1 and info["guarded_ops"] >= info["ops"] - 6
+        assert eng.regions_skipped() == 12                   # every other step (the clock falls)
+    assert info["acc_operands"] > 0 and info["stores_elided"] > 0
+
+
+def test_serial_guard_is_per_warp_and_exact_with_lane_dependent_clocks():
+    """The enable differs between lanes (a per-lane gated clock): warps whose lanes are all idle
+    skip, the others execute - every lane must still match the oracle."""
+    def build_(M):
+        top = M.Composite()
+        top.add_child("en", M.ExposedPin(M.ExposedPin.IN, 1))
+        top.add_child("clk", M.Clock())
+        top.add_child("gclk", M.Gate(M.Gate.AND, 1, 2))
+        top.connect("clk", "out", "gclk", "in0")
+        top.connect("en", "", "gclk", "in1")
+        top.add_child("d", M.ExposedPin(M.ExposedPin.IN, 1))
+        n = 48
+        for i in range(n):
+            top.add_child(f"r{i}", M.Register(1))
+            top.add_child(f"x{i}", M.Gate(M.Gate.XOR, 1, 2))
+        top.add_child("q", M.ExposedPin(M.ExposedPin.OUT, 1))
+        for i in range(n):
+            top.connect("gclk", "out", f"r{i}", "clock")
+            top.connect("d" if i == 0 else f"r{i - 1}", "" if i == 0 else "out", f"x{i}", "in0")
+            top.connect("d", "", f"x{i}", "in1")
+            top.connect(f"x{i}", "out", f"r{i}", "data")
+        top.connect(f"r{n - 1}", "out", "q", "")
+        return top
+
+    lanes = 64 * 70                                      # three "warps" of 32 columns in the test double
+    en = np.zeros(lanes, dtype=np.uint64)
+    en[64 * 40:] = 1                                     # warp 0 fully idle, warp 1 mixed, warp 2 fully active
+    rng = np.random.default_rng(5)
+    from oracle import restate
+    root = build_(MD)
+    ora = restate.RestatedJIT(root, 1, True, lanes=lanes)
+    eng = serial_factory("ports", share_edge_detectors=True)(root, 1, lanes)
+    assert eng.program.serial_info["regions"] >= 1
+    for sim in (ora, eng):
+        sim.set_pin_state("/en/pin", en)
+    for step in range(12):
+        d = rng.integers(0, 2, size=lanes, dtype=np.uint64)
+        for sim in (ora, eng):
+            sim.set_pin_state("/d/pin", d)
+            sim.step()
+        assert np.array_equal(eng.get_pin_state("/q/pin", lanes=True), ora.get_pin_state("/q/pin", lanes=True)), step
+    assert eng.regions_skipped() == 12                   # warp 0 never runs the region
+
+
+def test_serial_stream_invariants():
+    prog = serial.compile_circuit_serial(circuits.lfsr_pipeline(MD, 4, 8, 30, taps=(7, 5, 1, 0)), keep="ports",
+                                         share_edge_detectors=True)
+    recs = list(serial.decode(prog.records))
+    assert len(recs) % serial.BLOCK == 0
+    n_slots = prog.n_persist + prog.n_scratch
+    for blk in range(0, len(recs), serial.BLOCK):
+        stored = set()
+        for r in recs[blk:blk + serial.BLOCK]:
+            if r["op"] == serial.OP_GUARD:
+                assert r["pos"] % serial.BLOCK == serial.BLOCK - 1           # last of its block
+                assert r["out"] % serial.BLOCK == 0 and r["pos"] + 1 + r["out"] <= len(recs)
+                continue
+            for k, kind in enumerate(r["kinds"]):
+                if kind == serial.K_EARLY:
+                    assert r["slots"][k] not in stored, "EARLY load of a slot stored earlier in the block"
+                if kind in (serial.K_EARLY, serial.K_LATE):
+                    assert r["slots"][k] < n_slots
+            if r["store"]:
+                stored.add(r["out"])
+                assert r["out"] < n_slots
+
+
+def test_compiling_one_design_twice_with_shared_edge_detectors_is_stable():
+    """lower(share_edge_detectors=True) used to rewrite design.net_sig in place, so a
+    second compile of the same Design put the leader's prevclock into recyclable scratch."""
+    design = compiler.flatten(circuits.lfsr_pipeline(MD, 3, 8, 10, taps=(7, 5, 1, 0)))
+    before = design.net_sig.copy()
+    a = compiler.compile_design(design, keep="ports", share_edge_detectors=True)
+    b = compiler.compile_design(design, keep="ports", share_edge_detectors=True)
+    c = compiler.compile_design(design, keep="ports", share_edge_detectors=False)
+    assert np.array_equal(design.net_sig, before)
+    assert (a.n_persist, a.n_scratch, a.n_gates) == (b.n_persist, b.n_scratch, b.n_gates)
+    assert np.array_equal(a.records, b.records) and np.array_equal(a.sig_slot, b.sig_slot)
+    assert np.array_equal(a.sig_kept, b.sig_kept)
+    assert c.n_gates > a.n_gates
+    lead = a.pin_slots("/l0_q0/prevclock")[0]                  # whichever pin leads, members view its slot
+    assert all(a.pin_slots(f"/l{n}_q{k}/prevclock")[0] == lead for n in range(3) for k in range(8))
+    assert lead < a.n_persist
