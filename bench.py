@@ -1,20 +1,26 @@
 #!/usr/bin/env python
 """bench.py - gate-evals/sec of the levelized evaluation hot path (BASELINE.json metric).
 
-Workload (N GPUs, weak scaling): BASELINE.json configs[4] - synthetic random levelized DAG,
-1M two-input gates, depth 200, 4096 primary inputs - on 2^23 stimulus lanes PER GPU (2^26
-lanes at 8 GPUs, the named configuration), netlist replicated, lanes sharded, one
-NCCL all-reduce (sum) of the per-GPU output signatures per step.  One "step" = one
-evaluation pass of the whole netlist over every lane of the rank's shard + its signature.
+Headline workload (N GPUs, weak scaling): BASELINE.json configs[4] - synthetic random levelized
+DAG, 1M two-input gates, depth 200, 4096 primary inputs - on 2^23 stimulus lanes PER GPU (2^26
+lanes at 8 GPUs, the named configuration), netlist replicated, lanes sharded, one NCCL
+all-reduce (sum) of the per-GPU output signatures per step.  One "step" = one evaluation pass of
+the whole netlist over every lane of the rank's shard + its signature.
 
   python bench.py [--gpus N --steps K --warmup W]            our engine (CUDA, sm_100a)
-  python bench.py --impl reference [...]                      the reference algorithm on the host
-                                                              cores (oracle port, all threads),
-                                                              bounded sample of the same workload
+  python bench.py --impl reference [...]                      the reference's own LLVM JIT
+                                                              (baseline/_ref, 1 core) + the oracle's
+                                                              C port on all host threads
 
-Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+Prints ONE JSON line (rank 0).  Besides the base contract it carries
+  verify        default-on parity spot check of THIS run's outputs against the oracle (rc != 0 if false)
+  roofline      the level kernel K1 against the measured HBM copy peak
+  cpu_baseline  port = oracle/mcref.c on all host threads; jit = the reference's JIT.burst(), 1 core
+  configs       BASELINE.json configs C1-C4, measured in the same process after the headline
+See DESIGN.md "Measurement" for every field.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -27,6 +33,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "gate_evals_per_sec"
 UNIT = "gate-evals/s"
+JIT_CASES_C5 = ("c5_1000_20_w1", "c5_1000_20_w64", "c5_10000_50_w1", "c5_10000_50_w64")
+JIT_CASES_SMALL = ("c1", "c2_w1", "c2_w64")
 
 
 def parse():
@@ -43,10 +51,15 @@ def parse():
     ap.add_argument("--mode", default="levels", choices=["levels", "resident", "auto"])
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU baseline duration")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle spot check (it is outside the timed region)")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs C1-C4")
+    ap.add_argument("--no-jit", action="store_true", help="do not time the reference JIT beside the run")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="target duration of the C-port baseline")
+    ap.add_argument("--jit-seconds", type=float, default=2.0, help="burst() timing window per JIT case")
+    ap.add_argument("--c4-steps", type=int, default=20_000, help="steps of config C4 in the configs array (full size: 200000)")
     ap.add_argument("--streams", type=int, default=0, help="compute streams that independent tiles alternate over (0 = engine default)")
     ap.add_argument("--tune", default="", help="comma list key=value for mcb_set_tuning")
-    ap.add_argument("--verify", action="store_true", help="check sampled columns against the oracle")
+    ap.add_argument("--verify", action="store_true", help=argparse.SUPPRESS)     # round-1 flag; verification is default-on now
     return ap.parse_args()
 
 
@@ -102,51 +115,113 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-# CPU baseline / reference arm: the oracle port (plain C restatement of the reference's
-# sequential in-place evaluation) on the host cores, bounded sample of the same workload
+# the reference's own JIT, timed beside the run (one core per case, the reference is single-threaded)
 # ------------------------------------------------------------------------------------------------
-def cpu_baseline(a, root, seconds, rounds=1, mem_bytes=6 << 30):
-    """Time oracle/mcref.c (the reference's sequential in-place pass, many lanes wide) on all
-    host threads.  The oracle keeps one row per NET for every lane word (the reference's model:
-    one global per net, nothing recycled), so the sample's lanes are bounded by memory and the
-    sample's duration is reached by repeating full passes over it."""
-    import numpy as np
-    from oracle import cref, restate
+class JitWorkers:
+    """One `baseline/jit_worker.py` process per case.  They build right away (the 10^4-gate builds
+    take over a minute of Python flattening + LLVM codegen each) and then WAIT; `release()` lets
+    them time `burst()` - called when this process is not hammering the host cores itself."""
+
+    def __init__(self, cases, seconds):
+        self.procs = {}
+        worker = os.path.join(ROOT, "baseline", "jit_worker.py")
+        for c in cases:
+            try:
+                self.procs[c] = subprocess.Popen([sys.executable, worker, c, "--seconds", str(seconds), "--wait"],
+                                                 stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+                                                 stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                pass
+
+    def release(self):
+        for p in self.procs.values():
+            try:
+                p.stdin.write("go\n")
+                p.stdin.flush()
+            except Exception:
+                pass
+
+    def collect(self, timeout=420.0):
+        out, deadline = {}, time.time() + timeout
+        for c, p in self.procs.items():
+            try:
+                stdout, _ = p.communicate(timeout=max(1.0, deadline - time.time()))
+                lines = [json.loads(l) for l in stdout.splitlines() if l.startswith("{")]
+                out[c] = lines[-1] if lines else {"case": c, "unavailable": "worker printed nothing"}
+            except subprocess.TimeoutExpired:
+                p.kill()
+                out[c] = {"case": c, "unavailable": "JIT build did not finish within the bench's time limit"}
+            except Exception as exc:
+                out[c] = {"case": c, "unavailable": repr(exc)}
+        return out
+
+
+def jit_note():
+    return ("the reference's LLVM JIT (baseline/_ref/core/simulator.py:174-297, unmodified, llvmlite shim), burst() timed on ONE "
+            "core - the reference has no threads; width=1 is its ordinary single-instance mode, width=64 its best native mode "
+            "(64 lanes per gate op).  A 10^6-gate JIT cannot be built (SURVEY Q13: 5x10^4 gates = 284 s of LLVM codegen, "
+            "2x10^5 did not finish in 25 min), so the same generator is timed at 10^3 and 10^4 gates")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU port: the oracle's plain-C restatement of the reference's sequential in-place pass
+# ------------------------------------------------------------------------------------------------
+def make_port(a, root, mem_bytes=6 << 30):
+    """oracle/mcref.c on the full netlist.  The oracle keeps one row per NET for every lane word (the
+    reference's model: one global per net, nothing recycled), so the sample's lanes are bounded by
+    memory and its duration is reached by repeating full passes."""
+    from oracle import cref
     threads = os.cpu_count() or 1
     quantum = 8 * threads                                 # one 8-column block per thread
     n_rows = a.gates + a.inputs
     words = max(quantum, min(1 << 14, mem_bytes // (n_rows * 8)) // quantum * quantum)
-    sim = cref.CRef(root, 1, True, lanes=64 * words, threads=threads)
-    sim.set_rows(sim._base("/i0/pin"),
-                 restate.stimulus_word(np.arange(a.inputs)[:, None], np.arange(sim.words)[None, :]))
+    return cref.CRef(root, 1, True, lanes=64 * words, threads=threads)
+
+
+def port_stimulus(sim, a, cols):
+    """Row k of the inputs = stream k of the counter-based stimulus at global columns `cols`."""
+    import numpy as np
+    from oracle import restate
+    full = np.zeros((a.inputs, sim.words), dtype=np.uint64)
+    cols = np.asarray(cols, dtype=np.int64)
+    full[:, :len(cols)] = restate.stimulus_word(np.arange(a.inputs)[:, None], cols[None, :])
+    sim.set_rows(sim._base("/i0/pin"), full)
+
+
+def time_port(sim, a, seconds):
     sim.run(1)                                            # warm-up (first touch of the net file)
     t = time.perf_counter()
     sim.run(1)                                            # calibration
     dt = time.perf_counter() - t
     passes = int(max(1, min(200, round(seconds / max(dt, 1e-6)))))
-    times = []
-    for _ in range(rounds):
-        t = time.perf_counter()
-        sim.run(passes)
-        times.append(time.perf_counter() - t)
-    best = min(times)
-    value = a.gates * 64 * words * passes / best
-    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "full %d-gate netlist, %d lanes (%d of the %d lane words of one GPU shard), %d "
-                      "passes, oracle/mcref.c on %d threads, %.1f s" % (
-                          a.gates, 64 * words, words, a.lanes_per_gpu // 64, passes, threads, best),
-            "seconds": best, "times": times, "sim": sim, "passes": passes}
+    t = time.perf_counter()
+    sim.run(passes)
+    best = time.perf_counter() - t
+    value = a.gates * sim.lanes * passes / best
+    return {"value": value, "unit": UNIT, "cores": sim.threads, "kind": "port",
+            "value_per_core": value / sim.threads, "host_cpus": os.cpu_count(),
+            "sample": "full %d-gate netlist, %d lanes (%d of the %d lane words of one GPU shard), %d passes, "
+                      "oracle/mcref.c on %d threads, %.1f s" % (a.gates, sim.lanes, sim.words, a.lanes_per_gpu // 64,
+                                                                 passes, sim.threads, best),
+            "seconds": best, "same_config": False,
+            "same_config_note": "same netlist, bounded lane sample (a rate metric: gate-evals/s does not depend on the lane count "
+                                "once every thread has work)"}, passes
 
 
 def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from baseline import install_ref
+    install_ref.install()
+    # headline of this arm: the reference's JIT at the largest size of the C5 generator it can build
+    jit = JitWorkers(JIT_CASES_C5 if not a.no_jit else (), max(1.0, min(a.jit_seconds, 60.0 / max(1, a.steps + a.warmup))))
     from mcircuit_b200 import circuits
     root = circuits.random_dag(n_gates=a.gates, depth=a.depth, n_inputs=a.inputs)
-    per_step = max(1.0, min(15.0, 100.0 / max(1, a.steps + a.warmup)))
-    cb = cpu_baseline(a, root, per_step, rounds=1)
-    sim, passes = cb.pop("sim"), cb.pop("passes")
+    sim = make_port(a, root)
+    port_stimulus(sim, a, range(sim.words))
+    per_step = max(1.0, min(10.0, 60.0 / max(1, a.steps + a.warmup)))
+    port, passes = time_port(sim, a, per_step)
     times = []
     for i in range(a.warmup + a.steps):                   # one step = `passes` passes over the sample
         t = time.perf_counter()
@@ -155,22 +230,35 @@ def run_reference(a):
         if i >= a.warmup:
             times.append(dt)
     total = sum(times)
-    lanes = sim.lanes
-    value = a.gates * lanes * passes * len(times) / total
-    cb["value"] = value
-    cb.pop("times", None)
+    port["value"] = a.gates * sim.lanes * passes * len(times) / total
+    port["value_per_core"] = port["value"] / sim.threads
+    jit.release()
+    jits = jit.collect()
+    best = None
+    for c in ("c5_10000_50_w64", "c5_1000_20_w64"):
+        if c in jits and "value" in jits[c]:
+            best = jits[c]
+            break
+    if best is not None:
+        value, kind, ms = best["value"], "reference_jit", 1e3 * best["seconds"] / max(1, best["burst_calls"])
+        sample = ("JIT.burst() of the C5 generator at %d gates, width=%d, %d steps in %.2f s on 1 core (the reference "
+                  "cannot build 10^6 gates)" % (best["gates"], best["width"], best["steps"], best["seconds"]))
+        cores = 1
+    else:
+        value, kind, ms, sample, cores = port["value"], "port", 1e3 * total / len(times), port["sample"], port["cores"]
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": 1e3 * total / len(times),
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
         "data": "synthetic",
         "config": {"workload": workload_name(a), "gates": a.gates, "depth": a.depth, "inputs": a.inputs,
-                   "sample_lanes": lanes, "passes_per_step": passes, "host_threads": cb["cores"],
-                   "note": "reference algorithm (sequential in-place emit-order pass, "
-                           "core/simulator.py:195-223) as the oracle's plain-C port; the reference's "
-                           "own LLVM JIT cannot be built at 1M gates (SURVEY Q13) and is Python, so it "
-                           "does not travel to this box"},
-        "cpu_baseline": cb,
+                   "same_config": False,
+                   "note": "value = the reference's own LLVM JIT (one core) on the largest instance of the same generator it can "
+                           "build; cpu_baseline.port = the reference algorithm (sequential in-place emit-order pass, "
+                           "core/simulator.py:195-223) as the oracle's plain-C port on ALL host threads on the full 1M-gate "
+                           "netlist - a stronger baseline than the JIT in absolute terms"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+                         "host_cpus": os.cpu_count(), "jit": list(jits.values()), "jit_note": jit_note(), "port": port},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }))
@@ -202,6 +290,242 @@ def bind_to_gpu_numa_node(local):
         return None
 
 
+def build_info():
+    """What binary is being timed: the sidecar written by mcircuit_b200/build.py says which source
+    hash the shipped .so was compiled from; it must equal the hash of the tracked source."""
+    from mcircuit_b200 import build as _b
+    info = _b.read_buildinfo() or {}
+    try:
+        so_sha = hashlib.sha256(open(_b.OUT, "rb").read()).hexdigest()[:16]
+    except Exception:
+        so_sha = None
+    return {"source_sha16": _b.source_sha(), "built_from_source_sha16": info.get("source_sha16"),
+            "so_sha16": so_sha, "so_sha16_at_build": info.get("so_sha16"),
+            "matches_tracked_source": info.get("source_sha16") == _b.source_sha() and so_sha == info.get("so_sha16"),
+            "rebuilt_in_this_run": bool(getattr(_b, "rebuilt_in_this_process", False)),
+            "nvcc": info.get("nvcc"), "flags": info.get("flags"), "built_on": info.get("when")}
+
+
+def verify_c5(a, eng, rank, words, sim=None):
+    """Parity of THIS run: sampled lane columns of this rank's shard, spread over every compute
+    stream's tiles (first / middle / last tile, both planes), all outputs, bit for bit against the
+    oracle's C restatement fed the same counter-based stimulus."""
+    import numpy as np
+    from oracle import cref
+    tw, nt = eng.tile_words, eng.n_tiles
+    picks = [0, 1, tw - 1, tw, 2 * tw - 1 if nt > 1 else words // 3, (nt // 2) * tw + 7, (nt // 2 + 1) * tw + tw // 2,
+             words - tw - 1, words - 2, words - 1]
+    cols = np.array(sorted({int(c) % words for c in picks}), dtype=np.int64)
+    if sim is None:
+        sim = cref.CRef(eng.root, 1, True, lanes=64 * max(8, (len(cols) + 7) // 8 * 8), threads=1)
+    port_stimulus(sim, a, cols + rank * words)
+    sim.run(1)
+    pins = eng.output_pins()
+    want = sim.rows(sim._base(pins[0]), len(pins))[:, :len(cols)]
+    got = eng.sample_planes(pins, cols)
+    ok = bool(np.array_equal(got, want))
+    return {"bit_exact": ok, "columns": cols.tolist(), "tiles_touched": sorted({int(c) // tw for c in cols}),
+            "streams_touched": sorted({(int(c) // tw) % eng.n_streams for c in cols}),
+            "outputs_checked": len(pins), "words_compared": int(got.size),
+            "against": "oracle/mcref.c (C restatement of core/simulator.py:195-223), same splitmix64 stimulus"}, sim
+
+
+def run_configs(a, dev, world, rank, jits):
+    """BASELINE.json configs C1-C4 on this GPU, each checked against the oracle and timed with CUDA
+    events; at N > 1 every rank runs the same per-GPU shard (weak scaling) and the slowest rank counts."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from mcircuit_b200 import circuits
+    from mcircuit_b200.engine import B200Engine
+    from oracle import cref, restate
+    peak = hbm_peak()[0]
+    out = []
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize(dev)
+        best = 1e30
+        for _ in range(reps):
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        if world > 1:
+            t = torch.tensor([best], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            best = float(t[0])
+        return best
+
+    def all_ok(ok):
+        if world > 1:
+            t = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return bool(int(t[0]))
+        return bool(ok)
+
+    def port_rate(root, lanes, steps, threads=None):
+        sim = cref.CRef(root, 1, True, lanes=lanes, threads=threads)
+        sim.run(1)
+        t = time.perf_counter()
+        sim.run(steps)
+        dt = time.perf_counter() - t
+        return sim, dt
+
+    def entry(name, eng, lanes, steps, ms, bound, parity, scales, extra=None):
+        g = eng.program.n_gates
+        alg = eng.algorithmic_bytes(steps) / (ms * 1e-3) / 1e9
+        e = {"name": name, "mode": eng.mode, "lanes_per_gpu": lanes, "lanes_total": lanes * (world if scales else 1),
+             "steps": steps, "gates": g, "ms": ms, "ms_per_step": ms / steps,
+             "value": g * lanes * (world if scales else 1) * steps / (ms * 1e-3), "unit": UNIT,
+             "roofline": {"bound": bound, "achieved_GBps_algorithmic": alg, "frac_of_hbm_peak": alg / peak},
+             "parity": parity, "scales_with_gpus": scales}
+        if extra:
+            e.update(extra)
+        out.append(e)
+        return e
+
+    # ---- C1: examples/counter.py, 1,000 cycles = 2,000 steps, single instance ---------------------------
+    root = circuits.counter_circuit()
+    eng = B200Engine(root, 501, True, lanes=64, device=dev.index, mode="serial")
+    ora = restate.RestatedJIT(root, 501, True)
+    eng.run(2000)
+    for _ in range(2000):
+        ora.step()
+    pins = ("/clk/out", "/r/out", "/r/prevclock")
+    ok = all(eng.get_pin_state(p) == ora.get_pin_state(p) for p in pins)
+    eng.burst()
+    ora.burst()
+    ok = ok and all(eng.get_pin_state(p) == ora.get_pin_state(p) for p in pins)
+    ms = timed(lambda: eng.run(2000))
+    e = entry("C1 examples/counter.py clocked counter, 1,000 cycles (2,000 steps), single instance", eng, 64, 2000, ms,
+              "latency (one warp walks 4 micro-ops per step; nothing to parallelise in a single instance)",
+              {"bit_exact": all_ok(ok), "against": "oracle/restate.py after 2,000 steps and after burst() (502 more)", "pins": list(pins)},
+              False, {"lanes_note": "the reference's single instance is lane 0 of one 64-lane word; replicas only at N > 1"})
+    if rank == 0:
+        sim, dt = port_rate(root, 64, 200_000, threads=1)
+        e["cpu_port"] = {"value": 4 * 64 * 200_000 / dt, "cores": 1, "kind": "port", "sample": "64 lanes, 200,000 steps"}
+        e["cpu_jit"] = jits.get("c1")
+    del eng
+
+    # ---- C2: 32-bit ripple-carry adder, 2^20 vectors, one combinational step -----------------------------
+    lanes = 1 << 20
+    root = circuits.ripple_adder(nbits=32)
+    eng = B200Engine(root, 1, True, lanes=lanes, device=dev.index, mode="serial", keep="ports", lane_word_offset=rank * (lanes // 64))
+    eng.randomize_inputs()
+    eng.step()
+    planes = {p: eng.get_pin_planes(p)[0] for p in eng.input_pins() + eng.output_pins()}
+    carry = planes["/cin/pin"].copy()
+    ok = True
+    for k in range(32):                                   # a + b + cin, bit-sliced, on ALL 2^20 lanes
+        x, y = planes["/a%d/pin" % k], planes["/b%d/pin" % k]
+        ok = ok and np.array_equal(planes["/s%d/pin" % k], x ^ y ^ carry)
+        carry = (x & y) | (carry & (x ^ y))
+    ok = ok and np.array_equal(planes["/cout/pin"], carry)
+    ms = timed(lambda: eng.run(1), reps=5)
+    io_bytes = (65 + 33) * (lanes // 64) * 8
+    e = entry("C2 32-bit ripple-carry adder (160 gates), 2^20 random vectors, one step", eng, lanes, 1, ms,
+              "latency + compulsory I/O (65 dependent micro-op levels; %.1f MB of operand and result rows)" % (io_bytes / 1e6),
+              {"bit_exact": all_ok(ok), "against": "a + b + cin recomputed bit-sliced in numpy on all 2^20 lanes (sum and true carry-out)"},
+              True, {"compulsory_io_GBps": io_bytes / (ms * 1e-3) / 1e9})
+    if rank == 0:
+        sim, dt = port_rate(root, 1 << 20, 4)
+        e["cpu_port"] = {"value": 160 * (1 << 20) * 4 / dt, "cores": sim.threads, "kind": "port", "sample": "2^20 lanes, 4 passes"}
+        e["cpu_jit"] = [jits.get("c2_w1"), jits.get("c2_w64")]
+    del eng
+    torch.cuda.empty_cache()
+
+    # ---- C3: 64x64 array multiplier, 2^24 vectors, one step -------------------------------------------------
+    lanes = 1 << 24
+    root = circuits.array_multiplier(n=64)
+    eng = B200Engine(root, 1, True, lanes=lanes, device=dev.index, mode="levels", keep="ports", lane_word_offset=rank * (lanes // 64))
+    eng.randomize_inputs()
+    eng.step()
+    words = lanes // 64
+    cols = np.array([0, 1, words // 2, words - 1], dtype=np.int64)
+
+    def sample(pins):
+        return eng.sample_planes(pins, cols)
+    ia, ib = ["/a%d/pin" % k for k in range(64)], ["/b%d/pin" % k for k in range(64)]
+    po = ["/p%d/pin" % k for k in range(128)]
+    va, vb, vp = restate.unpack_lanes(sample(ia)), restate.unpack_lanes(sample(ib)), sample(po)
+    plo, phi = restate.unpack_lanes(vp[:64]), restate.unpack_lanes(vp[64:])
+    ok = all((int(x) * int(y)) == (int(h) << 64 | int(l)) for x, y, l, h in zip(va, vb, plo, phi))
+    ms = timed(lambda: eng.run(1))
+    e = entry("C3 64x64 array multiplier (24,064 gates), 2^24 random vectors bit-sliced, one step", eng, lanes, 1, ms,
+              "hbm (level kernel; a level is ~64 gates, the previous level's rows are still in L2)",
+              {"bit_exact": all_ok(ok), "against": "a * b in Python integers on %d sampled lanes (4 lane words of this shard)" % len(va)}, True)
+    if rank == 0:
+        sim, dt = port_rate(root, 1 << 16, 2)
+        e["cpu_port"] = {"value": eng.program.n_gates * (1 << 16) * 2 / dt, "cores": sim.threads, "kind": "port", "sample": "2^16 lanes, 2 passes"}
+        e["cpu_jit"] = {"unavailable": "the hierarchical 64x64 build takes 138 s of reference JIT build time (see tests/golden: its result is pinned there); not repeated per bench run"}
+    del eng
+    torch.cuda.empty_cache()
+
+    # ---- C4: 256 LFSRs + 1,000-register pipeline, state resident on the device ------------------------------
+    lanes = 1 << 20
+    steps = a.c4_steps
+    root = circuits.lfsr_pipeline()
+    eng = B200Engine(root, 1, True, lanes=lanes, device=dev.index, mode="serial", keep="ports", share_edge_detectors=True,
+                     lane_word_offset=rank * (lanes // 64))
+    seeds = ["/l%d_q%d/out" % (n, b) for n in range(256) for b in (0, 5, 17)]
+    eng.randomize_inputs(seeds)
+    eng.rt.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    eng.run(steps)                                        # ONE launch, no host round trip
+    e1.record()
+    torch.cuda.synchronize(dev)
+    launches = eng.rt.launch_count()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+    words = lanes // 64
+    cols = np.array([0, 1, 2, 3, words // 2, words // 2 + 1, words - 2, words - 1], dtype=np.int64)
+    sim = cref.CRef(root, 1, True, lanes=64 * 8)
+    for s, p in enumerate(seeds):
+        sim.set_planes(p, restate.stimulus_word(s, cols + rank * words)[None, :])
+    sim.run(steps)
+    probes = ["/pipe_out/pin"] + ["/tap%d/pin" % n for n in range(0, 256, 15)]
+    got = eng.sample_planes(probes, cols)
+    ok = all(np.array_equal(got[k], sim.planes(p)[0]) for k, p in enumerate(probes))
+    e = entry("C4 256 LFSRs + 1,000-register pipeline, %d clock cycles (%d steps) of the 10^5 named, 2^20 lanes, state resident"
+              % (steps // 2, steps), eng, lanes, steps, ms,
+              "hbm on rising steps (every register row read and written once), idle steps skipped (event-driven: the clock's "
+              "falling phase is the identity on every register)",
+              {"bit_exact": all_ok(ok), "against": "oracle/mcref.c run for the same %d steps on 8 sampled lane words (512 lanes), "
+                                                   "pipe_out and 18 LFSR taps" % steps,
+               "register_note": "Register parity is unpinned by the reference (its emitter does not compile, SURVEY Q3)"}, True,
+              {"launches": int(launches), "regions_skipped_by_warp0": eng.regions_skipped(),
+               "micro_ops_note": "gates counts the micro-ops executed with shared clock edge detectors (10,707); the unshared "
+                                 "lowering has 29,089", "serial": eng.program.serial_info,
+               "full_size_note": "--c4-steps 200000 runs all 10^5 cycles; tests/test_gpu_configs.py::test_c4_full_run_10e5_cycles does so on every gpu test run"})
+    if rank == 0:
+        sim2, dt = port_rate(root, 1 << 16, 20)
+        e["cpu_port"] = {"value": 29089 * (1 << 16) * 20 / dt, "cores": sim2.threads, "kind": "port",
+                         "sample": "2^16 lanes, 20 steps, 29,089 micro-ops per step (no sharing in the port)",
+                         "steps_per_s_at_2^16_lanes": 20 / dt}
+        e["cpu_jit"] = {"unavailable": "Register does not compile in the reference (core/simulator.py:121-126, SURVEY Q3)"}
+    del eng
+    torch.cuda.empty_cache()
+    return out
+
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
 def run_ours(a):
     import numpy as np
     import torch
@@ -225,6 +549,10 @@ def run_ours(a):
         ge.build()
     if world > 1:
         dist.barrier()
+    jit = None
+    if rank == 0 and not a.no_jit and not a.no_cpu_baseline:
+        cases = JIT_CASES_C5 + (JIT_CASES_SMALL if not a.no_configs else ())
+        jit = JitWorkers(cases, a.jit_seconds)            # they build while the GPU works, then wait
     from mcircuit_b200 import circuits
     from mcircuit_b200.engine import B200Engine
 
@@ -288,32 +616,52 @@ def run_ours(a):
     total_lanes = a.lanes_per_gpu * world
     value = prog.n_gates * total_lanes * a.steps / (ms * 1e-3)
 
+    # ---- parity of this very run (outside the timed region), every rank's shard -------------------------
+    verify, port_sim = None, None
+    if not a.no_verify:
+        if rank == 0 and world == 1 and not a.no_cpu_baseline:
+            port_sim = make_port(a, root)                # one oracle instance serves the check and the CPU baseline
+        verify, _ = verify_c5(a, eng, rank, words, port_sim)
+        if world > 1:
+            t = torch.tensor([1 if verify["bit_exact"] else 0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            verify["bit_exact_all_ranks"] = bool(int(t[0]))
+            verify["ranks_checked"] = world
+        else:
+            verify["bit_exact_all_ranks"] = verify["bit_exact"]
+            verify["ranks_checked"] = 1
+
     # ---- roofline of the dominant kernel (k_eval_level), measured live ------------------------------
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = hbm_peak()
     level_launches = prog.n_levels * eng.n_tiles            # per step per GPU
     alg_bytes_step = eng.algorithmic_bytes(1)               # this GPU, one step
-    avg_launch_s = (eval_total * 1e-3) / (a.steps * level_launches)
-    achieved = (alg_bytes_step / level_launches) / avg_launch_s / 1e9
-    traffic = None
+    agg_launch_s = (eval_total * 1e-3) / (a.steps * level_launches)
+    achieved = (alg_bytes_step / level_launches) / agg_launch_s / 1e9
+    traffic = {}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.isfile(tp):
         try:
-            traffic = json.load(open(tp)).get("k_eval_level_dram_bytes_per_launch")
+            traffic = json.load(open(tp))
         except Exception:
-            traffic = None
+            traffic = {}
+    alg_launch = alg_bytes_step / level_launches
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_eval_level", "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes_step / level_launches,
-                "avg_launch_us": avg_launch_s * 1e6, "launches_per_step": level_launches,
+                "traffic": traffic.get("steady_dram_bytes_per_launch", traffic.get("k_eval_level_dram_bytes_per_launch")),
+                "traffic_cold": traffic.get("k_eval_level_dram_bytes_per_launch"),
+                "traffic_steady": traffic.get("steady_dram_bytes_per_launch"),
+                "traffic_source": traffic.get("steady_source", traffic.get("source")),
+                "kernel": "k_eval_level", "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_launch,
+                "aggregate_us_per_launch": agg_launch_s * 1e6, "launches_per_step": level_launches,
+                "isolated_kernel_us": traffic.get("isolated_kernel_us"),
                 "eval_share_of_step": eval_total / ms,
-                "note": "achieved counts ALGORITHMIC bytes (24 B per gate-word, SURVEY 8d); with %d-word tiles "
-                        "part of them is served by L2 (previous level's rows, recycled scratch slots), so frac "
-                        "can exceed 1 while real DRAM traffic stays below the peak - see traffic and "
-                        "profiles/r01_ncu_eval_level.md" % eng.tile_words}
+                "l2_ceiling_GBps": traffic.get("k1_all_l2_hits_GBps"),
+                "note": "achieved counts ALGORITHMIC bytes (24 B per gate-word, SURVEY 8d) over the AGGREGATE launch rate (two "
+                        "tiles overlap on two streams, so aggregate_us_per_launch is not one kernel's duration - see "
+                        "isolated_kernel_us); with %d-word tiles part of the bytes is served by L2 (previous level's rows, "
+                        "recycled scratch slots), so frac exceeds 1 while real DRAM traffic (traffic_steady) stays below the "
+                        "peak.  l2_ceiling_GBps is the same kernel with every fan-in row an L2 hit "
+                        "(profiles/r02_probe_k1_l2_ceiling.jsonl): the bound no tiling can pass" % eng.tile_words}
 
     # ---- e2e: host buffers in, host buffers out, copies inside the timed region ----------------------
     e2e = None
@@ -347,9 +695,13 @@ def run_ours(a):
             t = torch.tensor([ems], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t[0])
+        h2d, d2h = int(h_in.numel() * 8), int((h_out.numel() + h_sig.numel()) * 8)
         e2e = {"value": prog.n_gates * total_lanes * a.steps / (ems * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_in.numel() * 8), "d2h_bytes_per_step": int((h_out.numel() + h_sig.numel()) * 8),
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "ms_per_step": ems / a.steps,
+               "host_link_GBps_per_gpu": (h2d + d2h) / (ems / a.steps * 1e-3) / 1e9,
+               "host_link_GBps_all_gpus": world * (h2d + d2h) / (ems / a.steps * 1e-3) / 1e9,
+               "host_link_ceiling": traffic.get("host_copy_ceiling"),
                "api": "B200Engine.run_host(h_in, h_out) [tile-pipelined H2D / eval / D2H over the C ABI] "
                       "-> signature -> D2H (pinned host buffers)"}
         assert np.array_equal(h_sig.numpy().view(np.uint64), signature_host), "e2e signature differs from resident run"
@@ -360,57 +712,63 @@ def run_ours(a):
             pc = int(np.unpackbits(h_out[i].numpy().view(np.uint8)).sum())
             assert pc == int(local_sig[i]), "downloaded output plane %d does not match its signature" % i
         e2e["downloaded_planes_checked_against_signature"] = len(idx)
+        del h_in, h_out
 
-    # ---- optional parity spot-check against the oracle on sampled columns -----------------------------
-    verify = None
-    if a.verify and rank == 0:
-        from oracle import cref, restate
-        cols = np.array([0, 1, 7, words // 2, words - 1], dtype=np.int64)
-        sim = cref.CRef(root, 1, True, lanes=64 * 8, threads=1)
-        stim = restate.stimulus_word(np.arange(a.inputs)[:, None], (cols + rank * words)[None, :])
-        full = np.zeros((a.inputs, 8), dtype=np.uint64)
-        full[:, :len(cols)] = stim
-        sim.set_rows(sim._base("/i0/pin"), full)
-        sim.run(1)
-        want = sim.rows(sim._base("/o0/pin"), 1)
-        ok = True
-        for k, p in enumerate(eng.output_pins()):
-            got = eng.get_pin_planes(p)[0][cols]
-            if not np.array_equal(got, sim.planes(p)[0][:len(cols)]):
-                ok = False
-                break
-        verify = {"columns": cols.tolist(), "outputs_checked": len(eng.output_pins()), "bit_exact": ok}
+    c5_meta = {"levels": prog.n_levels, "tile_words": eng.tile_words, "tiles": eng.n_tiles,
+               "persistent_slots": prog.n_persist, "scratch_slots": prog.n_scratch, "mode": eng.mode, "streams": eng.n_streams}
+    n_gates = prog.n_gates
+    sig_sum = int(signature_host[:sig["n"]].sum())
+    eng.close()
+    del eng, buf
+    torch.cuda.empty_cache()
+
+    # ---- the reference's JIT (released now: the GPU-side host work is over) and configs C1-C4 -----------
+    jits = {}
+    if jit is not None:
+        jit.release()
+        jits = jit.collect()
+    configs = None
+    if not a.no_configs:
+        configs = run_configs(a, dev, world, rank, jits)
 
     cb = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        cb = cpu_baseline(a, root, a.cpu_seconds)
-        for k in ("sim", "times", "passes"):
-            cb.pop(k, None)
+    if rank == 0 and not a.no_cpu_baseline:
+        if world == 1:
+            if port_sim is None:
+                port_sim = make_port(a, root)
+            port_stimulus(port_sim, a, range(port_sim.words))
+            cb, _ = time_port(port_sim, a, a.cpu_seconds)
+        else:
+            cb = {"kind": "port", "unavailable": "timed at N=1 only (the ranks' own host work would disturb it)"}
+        cb["port"] = dict(cb)
+        cb["jit"] = [jits[c] for c in JIT_CASES_C5 if c in jits]
+        cb["jit_note"] = jit_note()
+        cb["host_cpus"] = os.cpu_count()
 
+    ok = verify is None or verify["bit_exact_all_ranks"]
+    if configs:
+        ok = ok and all(c["parity"]["bit_exact"] for c in configs)
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "gates": prog.n_gates, "depth": a.depth,
-                       "inputs": a.inputs, "lanes_per_gpu": a.lanes_per_gpu, "lanes_total": total_lanes,
-                       "levels": prog.n_levels, "tile_words": eng.tile_words, "tiles": eng.n_tiles,
-                       "persistent_slots": prog.n_persist, "scratch_slots": prog.n_scratch,
-                       "mode": eng.mode, "streams": eng.n_streams, "parallelism": "lanes sharded x%d, netlist replicated" % world,
-                       "l2": "inputs larger than L2: %.1f GB of state streamed per step"
-                             % (alg_bytes_step / 1e9),
-                       "stimulus": "splitmix64 counter-based, generated on device",
-                       "compile_s": round(t_build, 1), "tuning": a.tune, "numa_node": numa},
-            "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "signature_popcount_sum": int(signature_host[:sig["n"]].sum()),
+            "config": dict({"workload": workload_name(a), "gates": n_gates, "depth": a.depth,
+                            "inputs": a.inputs, "lanes_per_gpu": a.lanes_per_gpu, "lanes_total": total_lanes,
+                            "parallelism": "lanes sharded x%d, netlist replicated" % world,
+                            "l2": "inputs larger than L2: %.1f GB of state streamed per step" % (alg_bytes_step / 1e9),
+                            "stimulus": "splitmix64 counter-based, generated on device",
+                            "compile_s": round(t_build, 1), "tuning": a.tune, "numa_node": numa}, **c5_meta),
+            "verify": verify, "roofline": roofline, "cpu_baseline": cb, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "signature_popcount_sum": sig_sum, "configs": configs, "build": build_info(),
         }
-        if verify is not None:
-            out["verify"] = verify
         print(json.dumps(out))
     if sampler:
         sampler.stop()
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)                                       # a fast result that differs from the reference's is not a result
 
 
 def main():

@@ -1,4 +1,13 @@
-"""Build libmcb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+"""Build libmcb200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Whether a rebuild is needed is decided by CONTENT, not by mtime: the sidecar
+``libmcb200.so.buildinfo`` records the hash of the sources the binary was compiled from (and the
+binary's own hash, the nvcc command and version).  A snapshot that carries a stale or foreign
+``.so`` is therefore rebuilt on the box that runs it, and ``bench.py`` prints both hashes so a
+reader can see that the timed binary was compiled from the tracked source."""
+import datetime
+import hashlib
+import json
 import os
 import shutil
 import subprocess
@@ -6,11 +15,14 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "mcb200.cu")
+HDR = os.path.join(os.path.dirname(HERE), "include", "mcb200.h")
 OUT = os.path.join(HERE, "libmcb200.so")
+INFO = OUT + ".buildinfo"
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
 ]
+rebuilt_in_this_process = False
 
 
 def nvcc_path():
@@ -20,23 +32,56 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def _sha(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()[:16]
+
+
+def source_sha():
+    h = hashlib.sha256()
+    for path in (SRC, HDR):
+        h.update(open(path, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()[:16]
+
+
+def read_buildinfo():
+    try:
+        return json.load(open(INFO))
+    except Exception:
+        return None
+
+
 def needs_build():
     if not os.path.isfile(OUT):
         return True
-    deps = [SRC, os.path.join(os.path.dirname(HERE), "include", "mcb200.h")]
-    return any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps)
+    info = read_buildinfo()
+    if info is None:
+        return True
+    return info.get("source_sha16") != source_sha() or info.get("so_sha16") != _sha(OUT)
 
 
 def build(force=False, verbose=False):
+    global rebuilt_in_this_process
     if not force and not needs_build():
         return OUT
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    try:
+        nvcc = nvcc_path()
+    except RuntimeError:
+        if os.path.isfile(OUT) and not force:
+            return OUT                               # no compiler on this box: run what was shipped (bench.py reports the mismatch)
+        raise
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed: %s" % " ".join(cmd))
     if verbose:
         sys.stderr.write(res.stderr)
+    ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()
+    json.dump({"source_sha16": source_sha(), "so_sha16": _sha(OUT), "nvcc": ver[-2] if len(ver) >= 2 else "",
+               "flags": " ".join(NVCC_FLAGS), "when": datetime.datetime.utcnow().isoformat() + "Z",
+               "host": os.uname().nodename}, open(INFO, "w"))
+    rebuilt_in_this_process = True
     return OUT
 
 

@@ -74,6 +74,8 @@ struct Tuning {
     int persist_block = 1024;   // threads per CTA of the persistent level kernel
     int serial_block = 128;     // threads per CTA of the serial kernel (warps are independent)
     int serial_word_bytes = 0;  // bytes of a lane column per thread (0: auto, 8, 4, 2, 1)
+    int serial_pf_l1 = 1;       // the stream's row prefetches go to L1 (1) or stop in L2 (0)
+    int serial_rec_ahead = 2;   // prefetch the record line this many blocks ahead into L1 (0: off)
 };
 static Tuning g_tune;
 static int g_sm_count = 0;
@@ -845,10 +847,15 @@ static int launch_resident(const uint4 *recs, int n_recs, const View &v, long lo
 enum { SK_NONE = 0, SK_EARLY = 1, SK_LATE = 2, SK_ACC = 3, SK_GREG = 4 };
 #define MCB_OP_GUARD 11
 
+__device__ __forceinline__ void ser_prefetch(const void *p, int l1) {
+    if (l1) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+    else asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
 template <typename W, bool UNIFIED>
 __global__ void __launch_bounds__(128)
 k_run_serial(const uint4 *__restrict__ recs, int n_recs, View v, long long steps, long long n_cols,
-             unsigned long long *__restrict__ skipped) {
+             unsigned long long *__restrict__ skipped, int pf_l1, int rec_ahead) {
     const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = col < n_cols;
     const unsigned warp_mask = __ballot_sync(0xffffffffu, active);
@@ -860,24 +867,85 @@ k_run_serial(const uint4 *__restrict__ recs, int n_recs, View v, long long steps
         int ip = 0;
         while (ip < n_recs) {
             uint4 r[SER_BLOCK];
-            W va[SER_BLOCK], vb[SER_BLOCK], vc[SER_BLOCK];
 #pragma unroll
             for (int u = 0; u < SER_BLOCK; ++u) r[u] = __ldg(recs + ip + u);
+            // the record line of a later block (one 128-byte line per block): the state traffic keeps
+            // pushing the stream out of L1, and a block cannot start before its records are there
+            if (rec_ahead) {
+                int nx = ip + rec_ahead * SER_BLOCK;
+                if (nx >= n_recs) nx -= n_recs;
+                if (nx < n_recs) asm volatile("prefetch.global.L1 [%0];" :: "l"(recs + nx));
+            }
+            // Block patterns (tagged by the host in record 0): the whole block as straight-line code.
+            const uint32_t pat = r[0].w >> 28, pat_id = (r[0].w >> 24) & 15u;
+            if (pat_id == 1) {
+                // up to 8 enabled registers in a row: out = G ? d : out.  The head takes d from the
+                // accumulator or from a row; every other stage takes the previous stage's NEW value
+                // (a shift chain under the reference's in-place order) - pure register forwarding.
+                W old[SER_BLOCK];
+                W d0 = acc;
+                if (((r[0].y >> 27) & 7u) == SK_EARLY) d0 = cols.ld(r[0].y & SER_M24);
+#pragma unroll
+                for (int u = 0; u < SER_BLOCK; ++u) {
+                    old[u] = 0;
+                    if (u < (int)pat) {
+                        old[u] = cols.ld(r[u].z & SER_M24);
+                        if (r[u].y >> 30) ser_prefetch(cols.at(r[u].x & SER_M24), pf_l1);
+                    }
+                }
+                acc = d0;
+#pragma unroll
+                for (int u = 0; u < SER_BLOCK; ++u) {
+                    if (u < (int)pat) {
+                        acc = (greg & acc) | ((W)~greg & old[u]);
+                        cols.st(r[u].z & SER_M24, acc);
+                    }
+                }
+                ip += SER_BLOCK;
+                continue;
+            }
+            if (pat_id == 2) {
+                // up to 4 register-pipeline stages: x = acc ^ row; out = G ? x : out
+                W old[SER_BLOCK / 2], q[SER_BLOCK / 2];
+#pragma unroll
+                for (int u = 0; u < SER_BLOCK / 2; ++u) {
+                    old[u] = q[u] = 0;
+                    if (u < (int)pat) {
+                        q[u] = cols.ld(r[2 * u].y & SER_M24);
+                        old[u] = cols.ld(r[2 * u + 1].z & SER_M24);
+                        if (r[2 * u].y >> 30) ser_prefetch(cols.at(r[2 * u].x & SER_M24), pf_l1);
+                        if (r[2 * u + 1].y >> 30) ser_prefetch(cols.at(r[2 * u + 1].x & SER_M24), pf_l1);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < SER_BLOCK / 2; ++u) {
+                    if (u < (int)pat) {
+                        const W x = acc ^ q[u];
+                        acc = (greg & x) | ((W)~greg & old[u]);
+                        cols.st(r[2 * u + 1].z & SER_M24, acc);
+                    }
+                }
+                ip += SER_BLOCK;
+                continue;
+            }
+            W va[SER_BLOCK], vb[SER_BLOCK], vc[SER_BLOCK];
 #pragma unroll
             for (int u = 0; u < SER_BLOCK; ++u) {
+                va[u] = vb[u] = vc[u] = 0;
+                if (u >= (int)pat) continue;                 // generic block: `pat` records are worth decoding
                 const uint32_t ka = (r[u].y >> 24) & 7u, kb = (r[u].y >> 27) & 7u, kc = (r[u].z >> 24) & 7u;
                 const uint32_t pf = r[u].y >> 30;
-                va[u] = vb[u] = vc[u] = 0;
                 if (ka == SK_EARLY) va[u] = cols.ld(r[u].x & SER_M24);
                 if (kb == SK_EARLY) vb[u] = cols.ld(r[u].y & SER_M24);
                 if (kc == SK_EARLY) vc[u] = cols.ld(r[u].z & SER_M24);
                 if (pf) {
                     const uint32_t slot = (pf == 1 ? r[u].x : (pf == 2 ? r[u].y : r[u].z)) & SER_M24;
-                    asm volatile("prefetch.global.L2 [%0];" :: "l"(cols.at(slot)));
+                    ser_prefetch(cols.at(slot), pf_l1);
                 }
             }
 #pragma unroll
             for (int u = 0; u < SER_BLOCK; ++u) {
+                if (u >= (int)pat) continue;
                 const uint32_t flags = r[u].x >> 24;
                 const uint32_t op = flags & 15u;
                 if (op == MCB_OP_NOP || op == MCB_OP_GUARD) continue;       // warp-uniform
@@ -920,8 +988,10 @@ static int launch_serial_w(const uint4 *recs, int n_recs, const View &v, long lo
         return fail(MCB_ERR_ARG, "row stride of 4 GB or more is not supported by the serial kernel");
     const bool unified = v.scratch_biased == nullptr ||
                          (v.scratch_biased == v.persist && v.sstride == v.pstride);
-    if (unified) k_run_serial<W, true><<<(unsigned)grid, block, 0, s>>>(recs, n_recs, v, steps, cols, d_skipped);
-    else k_run_serial<W, false><<<(unsigned)grid, block, 0, s>>>(recs, n_recs, v, steps, cols, d_skipped);
+    if (unified) k_run_serial<W, true><<<(unsigned)grid, block, 0, s>>>(recs, n_recs, v, steps, cols, d_skipped,
+                                                                        g_tune.serial_pf_l1, g_tune.serial_rec_ahead);
+    else k_run_serial<W, false><<<(unsigned)grid, block, 0, s>>>(recs, n_recs, v, steps, cols, d_skipped,
+                                                                  g_tune.serial_pf_l1, g_tune.serial_rec_ahead);
     LAUNCH_CHECK("k_run_serial");
     return 0;
 }
@@ -1102,6 +1172,8 @@ int mcb_set_tuning(const char *key, int value) {
     else if (!strcmp(key, "persist_block")) p = &g_tune.persist_block;
     else if (!strcmp(key, "serial_block")) p = &g_tune.serial_block;
     else if (!strcmp(key, "serial_word_bytes")) p = &g_tune.serial_word_bytes;
+    else if (!strcmp(key, "serial_pf_l1")) p = &g_tune.serial_pf_l1;
+    else if (!strcmp(key, "serial_rec_ahead")) p = &g_tune.serial_rec_ahead;
     else return fail(MCB_ERR_ARG, "unknown tuning key %s", key);
     int old = *p;
     *p = value;

@@ -466,6 +466,14 @@ class B200Engine(Executor):
             out[b] = self.rt.to_host_u64(self._plane[s * self.stride: s * self.stride + self.words])
         return out
 
+    def sample_planes(self, pins: Sequence[str], cols) -> np.ndarray:
+        """uint64[n_bits, len(cols)]: the lane words of every bit of ``pins`` at the lane-word columns
+        ``cols`` only - a gather of n_bits x len(cols) words, however wide the rows are."""
+        slots = np.asarray(self._flat_slots(pins), dtype=np.int64)
+        cols = np.asarray(cols, dtype=np.int64)
+        flat = slots[:, None] * self.stride + cols[None, :]
+        return self.rt.to_host_u64(self._plane[self.rt.to_device(flat.reshape(-1))]).reshape(len(slots), len(cols))
+
     # ---- stimulus / signatures --------------------------------------------------------------------------
     def input_pins(self) -> List[str]:
         """Root-level IN ports, in child order."""

@@ -29,7 +29,10 @@ Record: 16 bytes, four words of ``slot(24) | meta(8) << 24``:
   w0 = a slot   | op(4) | neg << 4 | store << 5 | keep_acc << 6
   w1 = b slot   | kind_a(3) | kind_b(3) << 3 | prefetch_field(2) << 6
   w2 = c slot   | kind_c(3)
-  w3 = out slot   (GUARD: number of records to jump)
+  w3 = out slot   (GUARD: number of records to jump); in the FIRST record of a block the top byte is the
+       block pattern: id(4) | units << 4 - 1 = up to 8 enabled registers ``MUX(G, acc | row, out) -> out``,
+       2 = up to 4 pipeline stages ``XOR(acc, row)`` + ``MUX(G, acc, out) -> out``; the kernel runs such a
+       block as straight-line code instead of decoding record by record
 """
 from __future__ import annotations
 
@@ -46,12 +49,14 @@ K_NONE, K_EARLY, K_LATE, K_ACC, K_GREG = 0, 1, 2, 3, 4
 BLOCK = 8
 SLOT_LIMIT = 1 << 24
 F_NEG, F_STORE, F_KEEP_ACC = 1 << 4, 1 << 5, 1 << 6
+_COMMUTATIVE2 = (2, 3, 4)   # AND, OR, XOR
+PAT_MUX, PAT_XM = 1, 2
 MIN_REGION = 32            # a guard costs a block boundary; shorter runs are not worth one
 COLD_DISTANCE = 512        # records since a row was last touched before a prefetch pays
 
 
 def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_detectors: bool = False,
-                   guard: bool = True, prefetch_distance: int = 64) -> Program:
+                   guard: bool = True, prefetch_distance: int = 64, patterns: bool = True) -> Program:
     """Lower ``design`` to a serial program.  ``keep`` / ``observe`` as in
     ``compiler.compile_design``; the result is a ``Program`` with ``serial=True`` whose
     ``records`` are the stream described in the module docstring."""
@@ -189,19 +194,47 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
         while len(layout) % BLOCK != mod_target:
             layout.append([NOPR, -1, -1])
 
+    # ---- block patterns: runs the kernel has straight-line code for (see k_run_serial) ------------------
+    #   'M'  MUX(G, d, out) -> out, the enabled register; d = the accumulator or a row
+    #   'X'  XOR(acc, row) whose only reader is the 'M' right behind it (a register pipeline stage)
+    cls = [""] * n_ops
+    if patterns:
+        for i in range(n_ops):
+            k = region_of[i]
+            if k >= 0 and code[i] == OP_MUX and A[i] == regions[k][2] and C[i] == OUT[i] and B[i] != regions[k][2]:
+                cls[i] = "M"
+        for i in range(1, n_ops - 1):
+            k = region_of[i]
+            if (k >= 0 and code[i] == OP_XOR and cls[i + 1] == "M" and region_of[i + 1] == k and B[i + 1] == OUT[i]
+                    and next_only(i) and n_reads[OUT[i]] >= 1 and i != regions[k][0]
+                    and ((A[i] == OUT[i - 1]) != (B[i] == OUT[i - 1])) and regions[k][2] not in (A[i], B[i])):
+                cls[i] = "X"
+                cls[i + 1] = "m"                     # second half of an X-M pair
+
     region_start = {r[0]: k for k, r in enumerate(regions)}
     region_end = {r[1]: k for k, r in enumerate(regions)}
     guard_pos: Dict[int, int] = {}
     after_region = set()                     # ops that must not take their operand from ACC
+    run_kind, run_fill = "", 0               # pattern run being laid out, units in its current block
     for i in range(n_ops):
         if i in region_end:
             pad_to(0)
             after_region.add(i)
+            run_kind = ""
         if i in region_start:
             k = region_start[i]
             pad_to(BLOCK - 1)
             guard_pos[k] = len(layout)
             layout.append([GUARDR, regions[k][2], k])
+            run_kind = ""
+        kind = {"M": "M", "X": "XM", "m": "XM"}.get(cls[i], "")
+        if cls[i] != "m":
+            cap = {"M": BLOCK, "XM": BLOCK // 2}.get(kind, 0)
+            if kind != run_kind or (kind and run_fill >= cap):
+                if kind or run_kind:
+                    pad_to(0)                        # pattern blocks start on a boundary and end in NOPs
+                run_kind, run_fill = kind, 0
+            run_fill += 1
         layout.append([REC, i, region_of[i]])
     pad_to(0)
     n_rec = len(layout)
@@ -312,6 +345,9 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
                     kinds[k] = K_EARLY
                     early_loads.append((p, slot))
                 touch.append((p, slot))
+        if base in _COMMUTATIVE2 and kinds[1] == K_ACC and kinds[0] != K_ACC:
+            kinds[0], kinds[1] = kinds[1], kinds[0]          # the accumulator operand goes first
+            slots[0], slots[1] = slots[1], slots[0]
         flags = base | (F_NEG if op & OP_NEG else 0)
         out_slot = 0
         if not elide[i]:
@@ -363,6 +399,43 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
             free_field[q] = 0
             n_prefetch += 1
 
+    # ---- tag the blocks that match a pattern exactly (the hint only selects straight-line code for the
+    # same records; a block that misses any precondition simply stays generic) ---------------------------
+    n_pat = {PAT_MUX: 0, PAT_XM: 0}
+    if patterns:
+        M24 = 0xFFFFFF
+        for b0 in range(0, n_rec, BLOCK):
+            blk = [[int(x) for x in rec[p]] for p in range(b0, b0 + BLOCK)]
+            fl = [w[0] >> 24 for w in blk]
+            last = max([q + 1 for q in range(BLOCK) if (fl[q] & 15) != OP_NOP] or [0])
+            rec[b0, 3] = int(rec[b0, 3]) | (last << 28)      # generic blocks: records worth decoding
+            n = 0
+            while n < BLOCK and (fl[n] & 15) != OP_NOP:
+                n += 1
+            if n == 0 or any((f & 15) != OP_NOP for f in fl[n:]):
+                continue
+            if any((w[1] >> 30) > 1 for w in blk[:n]):
+                continue                                     # a prefetch slot anywhere but field a
+
+            def is_m(w):
+                return ((w[0] >> 24) == (OP_MUX | F_STORE) and ((w[1] >> 24) & 7) == K_GREG and
+                        ((w[1] >> 27) & 7) in (K_ACC, K_EARLY) and ((w[2] >> 24) & 7) == K_EARLY and
+                        (w[2] & M24) == (w[3] & M24))
+
+            def is_x(w):
+                return ((w[0] >> 24) == OP_XOR and ((w[1] >> 24) & 7) == K_ACC and ((w[1] >> 27) & 7) == K_EARLY and
+                        ((w[2] >> 24) & 7) == K_NONE)
+
+            pat = 0
+            if all(is_m(w) for w in blk[:n]) and all(((w[1] >> 27) & 7) == K_ACC for w in blk[1:n]):
+                pat = PAT_MUX | (n << 4)                     # only the head of a chain takes its data from a row
+            elif n % 2 == 0 and all(is_x(blk[q]) and is_m(blk[q + 1]) and ((blk[q + 1][1] >> 27) & 7) == K_ACC
+                                    for q in range(0, n, 2)):
+                pat = PAT_XM | ((n // 2) << 4)
+            if pat:
+                rec[b0, 3] = (int(rec[b0, 3]) & 0xFFFFFF) | (pat << 24)
+                n_pat[pat & 15] += 1
+
     is_gate = np.asarray(ops.is_gate, dtype=bool)
     arity_tab = np.zeros(256, dtype=np.int64)
     for op, ar in OP_ARITY.items():
@@ -385,7 +458,8 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
     guarded = sum(e - b for b, e, _ in regions)
     prog.serial_info = {"records": n_rec, "ops": n_ops, "acc_operands": n_acc, "stores_elided": n_elided,
                         "late_loads": n_late, "prefetches": n_prefetch, "regions": len(regions),
-                        "guarded_ops": guarded, "padding": n_rec - n_ops - len(regions)}
+                        "guarded_ops": guarded, "padding": n_rec - n_ops - len(regions),
+                        "blocks": n_rec // BLOCK, "blocks_mux_chain": n_pat[PAT_MUX], "blocks_xor_mux": n_pat[PAT_XM]}
     return prog
 
 

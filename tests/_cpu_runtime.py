@@ -175,13 +175,31 @@ class CpuRuntime:
                 ip = 0
                 while ip < len(recs):
                     blk = recs[ip:ip + 8]
+                    pat_id, units = (blk[0][3] >> 24) & 15, blk[0][3] >> 28
+                    if pat_id == 1:          # the kernel's straight-line code for a chain of enabled registers
+                        old = [sub.read([blk[u][2] & M])[0] for u in range(units)]
+                        if ((blk[0][1] >> 27) & 7) == 1:
+                            acc = sub.read([blk[0][1] & M])[0]
+                        for u in range(units):
+                            acc = (greg & acc) | (~greg & old[u])
+                            sub.write([blk[u][2] & M], acc[None, :])
+                        ip += 8
+                        continue
+                    if pat_id == 2:          # ... and for register-pipeline stages
+                        q = [sub.read([blk[2 * u][1] & M])[0] for u in range(units)]
+                        old = [sub.read([blk[2 * u + 1][2] & M])[0] for u in range(units)]
+                        for u in range(units):
+                            acc = (greg & (acc ^ q[u])) | (~greg & old[u])
+                            sub.write([blk[2 * u + 1][2] & M], acc[None, :])
+                        ip += 8
+                        continue
                     early = {}
-                    for u, r in enumerate(blk):
+                    for u, r in enumerate(blk[:units]):
                         kinds = ((r[1] >> 24) & 7, (r[1] >> 27) & 7, (r[2] >> 24) & 7)
                         for k in range(3):
                             if kinds[k] == 1:
                                 early[(u, k)] = sub.read([r[k] & M])[0]
-                    for u, r in enumerate(blk):
+                    for u, r in enumerate(blk[:units]):
                         flags = r[0] >> 24
                         op = flags & 15
                         if op in (0, 11):
