@@ -96,17 +96,20 @@ int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void 
 int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
             const mcb_state *st, int64_t steps, int mode, void *stream);
 
-/* K3 v2 - serial run.  Replaces `step()` / `burst()` (core/simulator.py:195-245, :293-297) in
- * the reference's own execution model: every micro-op in emit order, in place, `steps` times,
- * each thread on its own (slice of a) lane column, one launch, no barrier.  `d_records` is a
- * serial stream (mcircuit_b200/serial.py): 16-byte records of four `slot(24) | meta(8) << 24`
- * words, a multiple of 8 records; operands come from memory (loaded a block of 8 records
- * ahead, or just in time when an earlier record of the block stores that slot), from the
- * accumulator (the previous record's result) or from the guard register; a GUARD record lets
- * a warp whose enable word is zero in every lane jump over the region it guards.
- * `word_bytes`: bytes of a lane word one thread owns (0 = automatic; 8, 4, 2 or 1).
- * `d_skipped`: optional device counter, += the guarded regions warp 0 jumped over.          */
-int mcb_run_serial(const uint32_t *d_records, int n_records, const mcb_state *st, int64_t steps,
+/* K3 v3 - streamed serial run.  Replaces `step()` / `burst()` (core/simulator.py:195-245, :293-297)
+ * in the reference's own execution model: every micro-op in emit order, in place, `steps` times,
+ * each consumer thread on its own (slice of a) lane column, ONE launch for any number of steps.
+ * `d_stream` (16-byte aligned) holds `n_blocks` control lines of 52 words (mcircuit_b200/serial.py):
+ * 4 meta words, 16 slots of the rows to stage, 8 records of four `field(24) | meta(8) << 24` words.
+ * A producer warp per CTA stages each block's control line and rows into a shared-memory ring
+ * with cp.async.bulk + mbarriers ahead of four consumer warps; operands come from the ring, from
+ * per-thread stash words in shared memory, from the accumulator (the previous record's result),
+ * from the guard register, or - for rows stored too recently to be staged - from an ordinary
+ * load; a GUARD record lets a CTA whose enable word is zero in every lane jump over its region.
+ * `word_bytes`: low byte = bytes of a lane word one thread owns (0 = 8; 8, 4, 2 or 1); bits 8.. =
+ * rows a ring group must hold (0 = 16, the format's maximum).
+ * `d_skipped`: optional device counter, += the guarded regions CTA 0 jumped over.             */
+int mcb_run_serial(const uint32_t *d_stream, int n_blocks, const mcb_state *st, int64_t steps,
                    int word_bytes, uint64_t *d_skipped, void *stream);
 
 /* K1g - mcb_eval_levels on the GROUPED stream: per level the records are sorted by base opcode

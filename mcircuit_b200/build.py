@@ -79,7 +79,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stderr)
     ver = subprocess.run([nvcc, "--version"], capture_output=True, text=True).stdout.strip().splitlines()
     json.dump({"source_sha16": source_sha(), "so_sha16": _sha(OUT), "nvcc": ver[-2] if len(ver) >= 2 else "",
-               "flags": " ".join(NVCC_FLAGS), "when": datetime.datetime.utcnow().isoformat() + "Z",
+               "flags": " ".join(NVCC_FLAGS), "when": datetime.datetime.now(datetime.timezone.utc).isoformat(),
                "host": os.uname().nodename}, open(INFO, "w"))
     rebuilt_in_this_process = True
     return OUT

@@ -507,3 +507,54 @@ def random_circuit(M=_own, seed=0, n_nodes=24, max_width=4, feedback=True, hiera
             probes.append(f"/out{k}/pin")
             k += 1
     return top, probes
+
+
+# ---- GUI-shaped circuits: what the reference GUI holds before Schematic.reconstruct (diagram.py:88-119) ----
+# Elements are LIBRARY entries (app.py:575-589: Input/Output pins and the seven gates, named
+# ``<kind>_<n>`` by element_factory, app.py:561-571); nets are the groups of pins joined by wires.
+def gui_full_adder(M=_own):
+    """1-bit full adder drawn with library gates, one unused NAND left on the sheet."""
+    ein, eout = M.ExposedPin(M.ExposedPin.IN), M.ExposedPin(M.ExposedPin.OUT)
+    elements = [("input_1", ein), ("input_2", ein), ("input_3", ein), ("xor_4", M.Gate(M.Gate.XOR)),
+                ("xor_5", M.Gate(M.Gate.XOR)), ("and_6", M.Gate(M.Gate.AND)), ("and_7", M.Gate(M.Gate.AND)),
+                ("or_8", M.Gate(M.Gate.OR)), ("output_9", eout), ("output_10", eout),
+                ("nand_11", M.Gate(M.Gate.AND, negated=True))]
+    nets = [
+        [("input_1", "pin"), ("xor_4", "in0"), ("and_7", "in0")],
+        [("input_2", "pin"), ("xor_4", "in1"), ("and_7", "in1")],
+        [("input_3", "pin"), ("xor_5", "in1"), ("and_6", "in1")],
+        [("xor_4", "out"), ("xor_5", "in0"), ("and_6", "in0")],
+        [("xor_5", "out"), ("output_9", "pin")],
+        [("and_6", "out"), ("or_8", "in0")],
+        [("and_7", "out"), ("or_8", "in1")],
+        [("or_8", "out"), ("output_10", "pin")],
+    ]
+    return elements, nets
+
+
+def gui_latch_and_ring(M=_own):
+    """Feedback drawn in the GUI: a cross-coupled NOR latch (set / reset inputs), a three-inverter
+    ring oscillator, and an XNOR of the two on an output - every value depends on the order in
+    which ``reconstruct`` adds children and edges."""
+    ein, eout = M.ExposedPin(M.ExposedPin.IN), M.ExposedPin(M.ExposedPin.OUT)
+    elements = [("input_1", ein), ("input_2", ein), ("nor_3", M.Gate(M.Gate.OR, negated=True)),
+                ("nor_4", M.Gate(M.Gate.OR, negated=True)), ("not_5", M.Not()), ("not_6", M.Not()), ("not_7", M.Not()),
+                ("xnor_8", M.Gate(M.Gate.XOR, negated=True)), ("output_9", eout), ("output_10", eout), ("output_11", eout)]
+    nets = [
+        [("input_1", "pin"), ("nor_3", "in0")],                     # reset
+        [("input_2", "pin"), ("nor_4", "in1")],                     # set
+        [("nor_3", "out"), ("nor_4", "in0"), ("output_9", "pin"), ("xnor_8", "in0")],     # q
+        [("nor_4", "out"), ("nor_3", "in1"), ("output_10", "pin")],                       # not q
+        [("not_5", "out"), ("not_6", "in")],
+        [("not_6", "out"), ("not_7", "in")],
+        [("not_7", "out"), ("not_5", "in"), ("xnor_8", "in1")],
+        [("xnor_8", "out"), ("output_11", "pin")],
+    ]
+    return elements, nets
+
+
+def gui_circuit(M=_own, name="full_adder"):
+    """The Composite ``Schematic.reconstruct`` builds for one of the GUI-shaped sheets above."""
+    from . import schematic
+    elements, nets = {"full_adder": gui_full_adder, "latch_and_ring": gui_latch_and_ring}[name](M)
+    return schematic.reconstruct(elements, nets, M=M)

@@ -74,8 +74,8 @@ struct Tuning {
     int persist_block = 1024;   // threads per CTA of the persistent level kernel
     int serial_block = 128;     // threads per CTA of the serial kernel (warps are independent)
     int serial_word_bytes = 0;  // bytes of a lane column per thread (0: auto, 8, 4, 2, 1)
-    int serial_pf_l1 = 1;       // the stream's row prefetches go to L1 (1) or stop in L2 (0)
-    int serial_rec_ahead = 2;   // prefetch the record line this many blocks ahead into L1 (0: off)
+    int stream_groups = 0;      // ring groups of the stream kernel (0: as many as fit, at most 24)
+    int stream_smem_kb = 0;     // shared memory the stream kernel may take per CTA (0: the device maximum)
 };
 static Tuning g_tune;
 static int g_sm_count = 0;
@@ -559,6 +559,33 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
 // UNIFIED: scratch rows follow the persistent rows with the same stride (single-tile runs), so
 // a row address is one 32x32+64 multiply-add on a per-thread base that already includes the
 // thread's column; otherwise the plane is picked by comparing with n_persist.
+template <typename W> __device__ __forceinline__ W ld_global_w(const W *p);
+template <> __device__ __forceinline__ uint64_t ld_global_w<uint64_t>(const uint64_t *p) {
+    uint64_t x; asm volatile("ld.global.u64 %0, [%1];" : "=l"(x) : "l"(p) : "memory"); return x;
+}
+template <> __device__ __forceinline__ uint32_t ld_global_w<uint32_t>(const uint32_t *p) {
+    uint32_t x; asm volatile("ld.global.u32 %0, [%1];" : "=r"(x) : "l"(p) : "memory"); return x;
+}
+template <> __device__ __forceinline__ uint16_t ld_global_w<uint16_t>(const uint16_t *p) {
+    uint16_t x; asm volatile("ld.global.u16 %0, [%1];" : "=h"(x) : "l"(p) : "memory"); return x;
+}
+template <> __device__ __forceinline__ uint8_t ld_global_w<uint8_t>(const uint8_t *p) {
+    uint32_t x; asm volatile("ld.global.u8 %0, [%1];" : "=r"(x) : "l"(p) : "memory"); return (uint8_t)x;
+}
+template <typename W> __device__ __forceinline__ void st_global_w(W *p, W x);
+template <> __device__ __forceinline__ void st_global_w<uint64_t>(uint64_t *p, uint64_t x) {
+    asm volatile("st.global.u64 [%0], %1;" :: "l"(p), "l"(x) : "memory");
+}
+template <> __device__ __forceinline__ void st_global_w<uint32_t>(uint32_t *p, uint32_t x) {
+    asm volatile("st.global.u32 [%0], %1;" :: "l"(p), "r"(x) : "memory");
+}
+template <> __device__ __forceinline__ void st_global_w<uint16_t>(uint16_t *p, uint16_t x) {
+    asm volatile("st.global.u16 [%0], %1;" :: "l"(p), "h"(x) : "memory");
+}
+template <> __device__ __forceinline__ void st_global_w<uint8_t>(uint8_t *p, uint8_t x) {
+    asm volatile("st.global.u8 [%0], %1;" :: "l"(p), "r"((uint32_t)x) : "memory");
+}
+
 template <typename W, bool UNIFIED>
 struct GlobalCols {
     char *base_p;                           // persist plane + this thread's column
@@ -571,14 +598,18 @@ struct GlobalCols {
         stride_p = (uint32_t)(v.pstride * 8);
         stride_s = (uint32_t)(v.sstride * 8);
         n_persist = v.n_persist;
+        // opaque to the optimiser: otherwise it rematerialises "kernel parameter + column offset" at every use
+        // (5-7 instructions per row address instead of one IMAD.WIDE on a base register)
+        asm volatile("" : "+l"(base_p), "+l"(base_s), "+r"(stride_p), "+r"(stride_s));
     }
     __device__ __forceinline__ W *at(uint32_t slot) const {
         if (UNIFIED) return reinterpret_cast<W *>(base_p + (unsigned long long)slot * stride_p);
         return reinterpret_cast<W *>(slot < n_persist ? base_p + (unsigned long long)slot * stride_p
                                                       : base_s + (unsigned long long)slot * stride_s);
     }
-    __device__ __forceinline__ W ld(uint32_t slot) const { return *at(slot); }
-    __device__ __forceinline__ void st(uint32_t slot, W x) const { *at(slot) = x; }
+    // explicit state space: the laundered base is a generic pointer to the compiler
+    __device__ __forceinline__ W ld(uint32_t slot) const { return ld_global_w<W>(at(slot)); }
+    __device__ __forceinline__ void st(uint32_t slot, W x) const { st_global_w<W>(at(slot), x); }
     // non-binding hint: safe even when an earlier batch still has to store to that row (a
     // thread's own store is ordered before its later load of the same address)
     __device__ __forceinline__ void prefetch(uint32_t slot) const {
@@ -830,169 +861,344 @@ static int launch_resident(const uint4 *recs, int n_recs, const View &v, long lo
 }
 
 // ------------------------------------------------------------------------------------------
-// K3 v2: serial run.  A thread owns (a slice of) one lane column and executes the reference's
-// step() exactly as the reference does - every micro-op in emit order, in place - for `steps`
-// steps, with no barrier of any kind (lanes never interact; warps are fully independent).
-// See mcircuit_b200/serial.py for the record format.  Per block of 8 records:
-//   phase 1: the 8 records (one 128-byte line, same address in every thread: a broadcast), every
-//            EARLY operand load of the block, and the L2 prefetches the records carry;
-//   phase 2: the records in order - LATE loads, accumulator / guard-register operands, the
-//            bitwise op, the store (elided when the next record is the only reader).
-// A GUARD record (always the last of its block) loads the region's enable word; when it is zero
-// in every lane of the warp, the warp jumps over the region: MUX(0, d, out) -> out and out ^= 0
-// are the identity, so skipping is exact (event-driven evaluation of idle clock phases).
+// K3 v3: streamed serial run (k_run_stream).  A consumer thread owns (a slice of) one lane column
+// and executes the reference's step() exactly as the reference does - every micro-op in emit
+// order, in place - for `steps` steps.  See mcircuit_b200/serial.py for the stream format and for
+// the rules that decide which rows may be staged ahead of time.
+//
+// CTA = 4 consumer warps (128 columns) + 1 producer warp.  The producer walks the stream ahead of
+// the consumers: per block of 8 records it stages the block's 208-byte control line and every
+// state row the block reads (one cp.async.bulk per row segment of 128 columns, each issued by its
+// own lane) into one of `n_groups` shared-memory ring groups, completion on the group's `full`
+// mbarrier; a group is reused when the four consumer warps have arrived on its `empty` mbarrier.
+// Consumers wait on `full`, run the records out of shared memory (operands: ring row, stash word,
+// accumulator, guard register, or - for rows the stream stored too recently to stage - an
+// ordinary load) and store results straight to global memory.  Nothing on the dependent chain
+// waits for L2 or HBM, and up to n_groups blocks of rows are in flight per SM.
+//
+// A GUARD record (last of its block) is a CTA-wide vote: every consumer warp publishes whether any
+// of its lanes has a non-zero enable, arrives on `guard_bar` and waits for the other warps; the
+// producer waits on the same barrier.  When the enable is zero everywhere, everybody jumps over the
+// region: MUX(0, d, out) -> out and out ^= 0 are the identity, so skipping is exact (event-driven
+// evaluation of idle clock phases); a warp that was out-voted runs the region with G = 0, which is
+// the same identity.  Consumers execute fence.proxy.async.global before they vote and at the start
+// of every FENCE block, which is what makes their earlier stores visible to later TMA reads.
 // ------------------------------------------------------------------------------------------
-#define SER_BLOCK 8
-#define SER_M24 0x00ffffffu
-enum { SK_NONE = 0, SK_EARLY = 1, SK_LATE = 2, SK_ACC = 3, SK_GREG = 4 };
+#define STR_BLOCK 8
+#define STR_RING_ROWS 16
+#define STR_WORDS 52                        // uint32 per control line
+#define STR_CTRL_BYTES 208
+#define STR_CTRL_PITCH 256
+#define STR_STASH 32
+#define STR_CONSUMER_WARPS 4
+#define STR_NT (32 * STR_CONSUMER_WARPS)    // columns per CTA
+#define STR_GB_MAX 24
+#define STR_PD 8                            // control lines the producer keeps in registers ahead of its issue point
+#define STR_HEAD_BYTES 1024                 // barriers and votes
+#define STR_M24 0x00ffffffu
+enum { TK_NONE = 0, TK_RING = 1, TK_LATE = 2, TK_ACC = 3, TK_GREG = 4, TK_STASH = 5 };
 #define MCB_OP_GUARD 11
 
-__device__ __forceinline__ void ser_prefetch(const void *p, int l1) {
-    if (l1) asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
-    else asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+
+struct StreamSmem {
+    uint64_t full[STR_GB_MAX];
+    uint64_t empty[STR_GB_MAX];
+    uint64_t guard_bar;
+    uint32_t votes[2][STR_CONSUMER_WARPS];
+};
+
+template <typename W, bool UNIFIED>
+__device__ __forceinline__ W stream_operand(uint32_t kind, uint32_t field, const W *rows, const W *stash,
+                                            const GlobalCols<W, UNIFIED> &cols, W acc, W greg, bool active) {
+    switch (kind) {
+        case TK_RING:  return rows[field * STR_NT];
+        case TK_LATE:  return active ? cols.ld(field) : (W)0;
+        case TK_ACC:   return acc;
+        case TK_GREG:  return greg;
+        case TK_STASH: return stash[field * STR_NT];
+        default:       return (W)0;
+    }
+}
+
+// Pattern 1, N enabled registers in a row: out = G ? d : out.  Ring row u holds the old value of
+// unit u and its slot (= the slot to store to) is fetch word u; the head takes d from wherever its
+// record says, every other stage takes the previous stage's NEW value (the reference's in-place
+// order) - pure register forwarding.  Straight-line: all shared-memory reads and address arithmetic
+// are hoisted above the dependent LOP3 chain by the compiler.
+template <typename W, bool UNIFIED, int N>
+__device__ __forceinline__ void stream_mux_chain(const uint4 *ctl, const W *rows, const W *stash, W *stash_w,
+                                                 const GlobalCols<W, UNIFIED> &cols, W &acc, W greg, bool active,
+                                                 bool has_stash) {
+    const uint32_t *slots = reinterpret_cast<const uint32_t *>(ctl + 1);
+    uint32_t out[N];
+    W old[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        out[u] = slots[u];
+        old[u] = rows[u * STR_NT];
+    }
+    const uint4 r0 = ctl[5];
+    W d = stream_operand<W, UNIFIED>((r0.y >> 27) & 7u, r0.y & STR_M24, rows, stash, cols, acc, greg, active);
+    W val[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        d = (greg & d) | ((W)~greg & old[u]);
+        val[u] = d;
+        if (active) cols.st(out[u], d);
+    }
+    acc = d;
+    if (has_stash) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const uint32_t so = reinterpret_cast<const uint32_t *>(ctl + 5 + u)[3] >> 24;
+            if (so) stash_w[(so - 1) * STR_NT] = val[u];
+        }
+    }
+}
+
+// Pattern 2, N register-pipeline stages: x = acc ^ q; out = G ? x : out.  Ring rows 2u / 2u+1 hold q and
+// the old value of stage u; fetch word 2u+1 is the slot to store to.
+template <typename W, bool UNIFIED, int N>
+__device__ __forceinline__ void stream_xor_mux(const uint4 *ctl, const W *rows, W *stash_w,
+                                               const GlobalCols<W, UNIFIED> &cols, W &acc, W greg, bool active,
+                                               bool has_stash) {
+    const uint32_t *slots = reinterpret_cast<const uint32_t *>(ctl + 1);
+    uint32_t out[N];
+    W q[N], old[N], val[N];
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        out[u] = slots[2 * u + 1];
+        q[u] = rows[(2 * u) * STR_NT];
+        old[u] = rows[(2 * u + 1) * STR_NT];
+    }
+    W d = acc;
+#pragma unroll
+    for (int u = 0; u < N; ++u) {
+        d = (greg & (d ^ q[u])) | ((W)~greg & old[u]);
+        val[u] = d;
+        if (active) cols.st(out[u], d);
+    }
+    acc = d;
+    if (has_stash) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) {
+            const uint32_t so = reinterpret_cast<const uint32_t *>(ctl + 6 + 2 * u)[3] >> 24;
+            if (so) stash_w[(so - 1) * STR_NT] = val[u];
+        }
+    }
 }
 
 template <typename W, bool UNIFIED>
-__global__ void __launch_bounds__(128)
-k_run_serial(const uint4 *__restrict__ recs, int n_recs, View v, long long steps, long long n_cols,
-             unsigned long long *__restrict__ skipped, int pf_l1, int rec_ahead) {
-    const long long col = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(32 * (STR_CONSUMER_WARPS + 1), 1)
+k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long long steps, long long n_cols,
+             long long ext_cols, unsigned long long *__restrict__ skipped, int n_groups, int ring_rows) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    StreamSmem *sh = reinterpret_cast<StreamSmem *>(smem);
+    W *stash_base = reinterpret_cast<W *>(smem + STR_HEAD_BYTES);
+    const uint32_t row_pitch = STR_NT * sizeof(W);
+    unsigned char *groups = smem + STR_HEAD_BYTES + STR_STASH * row_pitch;
+    const uint32_t group_bytes = STR_CTRL_PITCH + ring_rows * row_pitch;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long c0 = (long long)blockIdx.x * STR_NT;
+
+    if (tid == 0) {
+        for (int g = 0; g < n_groups; ++g) {
+            mbar_init(&sh->full[g], 1);
+            mbar_init(&sh->empty[g], STR_CONSUMER_WARPS);
+        }
+        mbar_init(&sh->guard_bar, STR_CONSUMER_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == STR_CONSUMER_WARPS) {
+        // ---------------- producer ----------------
+        long long left = ext_cols - c0;
+        const uint32_t row_bytes = (uint32_t)(left < STR_NT ? left : STR_NT) * (uint32_t)sizeof(W);
+        const char *pbase = reinterpret_cast<const char *>(v.persist) + c0 * (long long)sizeof(W);
+        const char *sbase = reinterpret_cast<const char *>(v.scratch_biased) + c0 * (long long)sizeof(W);
+        const unsigned long long pstride_b = (unsigned long long)v.pstride * 8ull, sstride_b = (unsigned long long)v.sstride * 8ull;
+        uint32_t g = 0, ph = 1, gph = 0, gidx = 0;   // ph: the parity that lets the first pass through a fresh barrier
+        // The control words of the next STR_PD blocks live in registers (lane j holds word j of each
+        // line): a line is read once and never in L1, so without this window every block would pay an
+        // L2 round trip on the issue path.  A jump over a skipped region refills the window.
+        uint32_t wq[STR_PD];
+        int b = 0, pb = 0;                       // block being issued / next block to prefetch
+        long long step = 0, pstep = 0;
+        bool refill = true;
+        while (step < steps) {
+            if (refill) {
+                pb = b;
+                pstep = step;
+#pragma unroll
+                for (int k = 0; k < STR_PD; ++k) {
+                    wq[k] = (pstep < steps && lane < 20) ? __ldg(stream + (size_t)pb * STR_WORDS + lane) : 0u;
+                    if (++pb == n_blocks) { pb = 0; ++pstep; }
+                }
+                refill = false;
+            }
+#pragma unroll
+            for (int k = 0; k < STR_PD; ++k) {
+                if (step >= steps || refill) break;
+                const uint32_t w = wq[k];
+                wq[k] = (pstep < steps && lane < 20) ? __ldg(stream + (size_t)pb * STR_WORDS + lane) : 0u;
+                if (++pb == n_blocks) { pb = 0; ++pstep; }
+                const uint32_t m0 = __shfl_sync(0xffffffffu, w, 0);
+                const uint32_t n_rows = m0 & 0xffu;
+                unsigned char *grp = groups + (size_t)g * group_bytes;
+                mbar_wait(&sh->empty[g], ph);
+                if (lane == 0) {
+                    mbar_expect_tx(&sh->full[g], STR_CTRL_BYTES + n_rows * row_bytes);
+                    bulk_g2s(grp, stream + (size_t)b * STR_WORDS, STR_CTRL_BYTES, &sh->full[g]);
+                }
+                __syncwarp();
+                if (lane >= 4 && lane < 4 + n_rows) {
+                    const uint32_t slot = w & STR_M24;
+                    const char *src = (UNIFIED || slot < v.n_persist) ? pbase + slot * pstride_b : sbase + slot * sstride_b;
+                    bulk_g2s(grp + STR_CTRL_PITCH + (lane - 4) * row_pitch, src, row_bytes, &sh->full[g]);
+                }
+                if (++g == (uint32_t)n_groups) { g = 0; ph ^= 1u; }
+                int nb = b + 1;
+                if (m0 & 0x100u) {                       // guard: follow the consumers' vote
+                    mbar_wait(&sh->guard_bar, gph);
+                    gph ^= 1u;
+                    const volatile uint32_t *vt = sh->votes[gidx];
+                    const uint32_t any = vt[0] | vt[1] | vt[2] | vt[3];
+                    gidx ^= 1u;
+                    if (!any) {
+                        nb += (int)__shfl_sync(0xffffffffu, w, 1);
+                        refill = true;
+                    }
+                }
+                b = nb;
+                if (b >= n_blocks) { b = 0; ++step; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const long long col = c0 + tid;
     const bool active = col < n_cols;
-    const unsigned warp_mask = __ballot_sync(0xffffffffu, active);
-    if (!active) return;
     const GlobalCols<W, UNIFIED> cols(v, col);
+    const W *stash = stash_base + tid;
+    W *stash_w = stash_base + tid;
     W acc = 0, greg = 0;
+    uint32_t g = 0, ph = 0, gph = 0, gidx = 0;
     unsigned long long n_skipped = 0;
     for (long long step = 0; step < steps; ++step) {
-        int ip = 0;
-        while (ip < n_recs) {
-            uint4 r[SER_BLOCK];
-#pragma unroll
-            for (int u = 0; u < SER_BLOCK; ++u) r[u] = __ldg(recs + ip + u);
-            // the record line of a later block (one 128-byte line per block): the state traffic keeps
-            // pushing the stream out of L1, and a block cannot start before its records are there
-            if (rec_ahead) {
-                int nx = ip + rec_ahead * SER_BLOCK;
-                if (nx >= n_recs) nx -= n_recs;
-                if (nx < n_recs) asm volatile("prefetch.global.L1 [%0];" :: "l"(recs + nx));
-            }
-            // Block patterns (tagged by the host in record 0): the whole block as straight-line code.
-            const uint32_t pat = r[0].w >> 28, pat_id = (r[0].w >> 24) & 15u;
-            if (pat_id == 1) {
-                // up to 8 enabled registers in a row: out = G ? d : out.  The head takes d from the
-                // accumulator or from a row; every other stage takes the previous stage's NEW value
-                // (a shift chain under the reference's in-place order) - pure register forwarding.
-                W old[SER_BLOCK];
-                W d0 = acc;
-                if (((r[0].y >> 27) & 7u) == SK_EARLY) d0 = cols.ld(r[0].y & SER_M24);
-#pragma unroll
-                for (int u = 0; u < SER_BLOCK; ++u) {
-                    old[u] = 0;
-                    if (u < (int)pat) {
-                        old[u] = cols.ld(r[u].z & SER_M24);
-                        if (r[u].y >> 30) ser_prefetch(cols.at(r[u].x & SER_M24), pf_l1);
-                    }
+        int b = 0;
+        while (b < n_blocks) {
+            unsigned char *grp = groups + (size_t)g * group_bytes;
+            mbar_wait(&sh->full[g], ph);
+            const uint4 *ctl = reinterpret_cast<const uint4 *>(grp);
+            const W *rows = reinterpret_cast<const W *>(grp + STR_CTRL_PITCH) + tid;
+            const uint4 m = ctl[0];
+            if (m.x & 0x200u) fence_async_global();
+            const uint32_t pat = (m.x >> 16) & 15u, units = (m.x >> 20) & 0xffu;
+            const bool has_stash = (m.x & 0x400u) != 0;
+            if (pat == 1) {
+#define MCB_MUX_CASE(N) case N: stream_mux_chain<W, UNIFIED, N>(ctl, rows, stash, stash_w, cols, acc, greg, active, has_stash); break;
+                switch (units) {
+                    MCB_MUX_CASE(8) MCB_MUX_CASE(7) MCB_MUX_CASE(6) MCB_MUX_CASE(5)
+                    MCB_MUX_CASE(4) MCB_MUX_CASE(3) MCB_MUX_CASE(2) MCB_MUX_CASE(1)
+                    default: break;
                 }
-                acc = d0;
-#pragma unroll
-                for (int u = 0; u < SER_BLOCK; ++u) {
-                    if (u < (int)pat) {
-                        acc = (greg & acc) | ((W)~greg & old[u]);
-                        cols.st(r[u].z & SER_M24, acc);
-                    }
+#undef MCB_MUX_CASE
+            } else if (pat == 2) {
+#define MCB_XM_CASE(N) case N: stream_xor_mux<W, UNIFIED, N>(ctl, rows, stash_w, cols, acc, greg, active, has_stash); break;
+                switch (units) {
+                    MCB_XM_CASE(4) MCB_XM_CASE(3) MCB_XM_CASE(2) MCB_XM_CASE(1)
+                    default: break;
                 }
-                ip += SER_BLOCK;
-                continue;
-            }
-            if (pat_id == 2) {
-                // up to 4 register-pipeline stages: x = acc ^ row; out = G ? x : out
-                W old[SER_BLOCK / 2], q[SER_BLOCK / 2];
+#undef MCB_XM_CASE
+            } else {
 #pragma unroll
-                for (int u = 0; u < SER_BLOCK / 2; ++u) {
-                    old[u] = q[u] = 0;
-                    if (u < (int)pat) {
-                        q[u] = cols.ld(r[2 * u].y & SER_M24);
-                        old[u] = cols.ld(r[2 * u + 1].z & SER_M24);
-                        if (r[2 * u].y >> 30) ser_prefetch(cols.at(r[2 * u].x & SER_M24), pf_l1);
-                        if (r[2 * u + 1].y >> 30) ser_prefetch(cols.at(r[2 * u + 1].x & SER_M24), pf_l1);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < SER_BLOCK / 2; ++u) {
-                    if (u < (int)pat) {
-                        const W x = acc ^ q[u];
-                        acc = (greg & x) | ((W)~greg & old[u]);
-                        cols.st(r[2 * u + 1].z & SER_M24, acc);
-                    }
-                }
-                ip += SER_BLOCK;
-                continue;
-            }
-            W va[SER_BLOCK], vb[SER_BLOCK], vc[SER_BLOCK];
-#pragma unroll
-            for (int u = 0; u < SER_BLOCK; ++u) {
-                va[u] = vb[u] = vc[u] = 0;
-                if (u >= (int)pat) continue;                 // generic block: `pat` records are worth decoding
-                const uint32_t ka = (r[u].y >> 24) & 7u, kb = (r[u].y >> 27) & 7u, kc = (r[u].z >> 24) & 7u;
-                const uint32_t pf = r[u].y >> 30;
-                if (ka == SK_EARLY) va[u] = cols.ld(r[u].x & SER_M24);
-                if (kb == SK_EARLY) vb[u] = cols.ld(r[u].y & SER_M24);
-                if (kc == SK_EARLY) vc[u] = cols.ld(r[u].z & SER_M24);
-                if (pf) {
-                    const uint32_t slot = (pf == 1 ? r[u].x : (pf == 2 ? r[u].y : r[u].z)) & SER_M24;
-                    ser_prefetch(cols.at(slot), pf_l1);
+                for (int u = 0; u < STR_BLOCK; ++u) {
+                    if (u >= (int)m.z) continue;                                  // records worth decoding
+                    const uint4 r = ctl[5 + u];
+                    const uint32_t flags = r.x >> 24;
+                    const uint32_t op = flags & 15u;
+                    if (op == MCB_OP_NOP || op == MCB_OP_GUARD) continue;         // uniform
+                    const W a = stream_operand<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
+                    const W bb = stream_operand<W, UNIFIED>((r.y >> 27) & 7u, r.y & STR_M24, rows, stash, cols, acc, greg, active);
+                    const W c = stream_operand<W, UNIFIED>((r.z >> 24) & 7u, r.z & STR_M24, rows, stash, cols, acc, greg, active);
+                    const W res = apply_op_w<W>(op | ((flags & 16u) << 3), a, bb, c);
+                    if ((flags & 32u) && active) cols.st(r.w & STR_M24, res);
+                    const uint32_t so = r.w >> 24;
+                    if (so) stash_w[(so - 1) * STR_NT] = res;
+                    acc = res;
                 }
             }
-#pragma unroll
-            for (int u = 0; u < SER_BLOCK; ++u) {
-                if (u >= (int)pat) continue;
-                const uint32_t flags = r[u].x >> 24;
-                const uint32_t op = flags & 15u;
-                if (op == MCB_OP_NOP || op == MCB_OP_GUARD) continue;       // warp-uniform
-                const uint32_t ka = (r[u].y >> 24) & 7u, kb = (r[u].y >> 27) & 7u, kc = (r[u].z >> 24) & 7u;
-                W a = va[u], b = vb[u], c = vc[u];
-                if (ka >= SK_LATE) a = (ka == SK_ACC) ? acc : (ka == SK_GREG ? greg : cols.ld(r[u].x & SER_M24));
-                if (kb >= SK_LATE) b = (kb == SK_ACC) ? acc : (kb == SK_GREG ? greg : cols.ld(r[u].y & SER_M24));
-                if (kc >= SK_LATE) c = (kc == SK_ACC) ? acc : (kc == SK_GREG ? greg : cols.ld(r[u].z & SER_M24));
-                W res = apply_op_w<W>(op | ((flags & 16u) << 3), a, b, c);
-                if (flags & 32u) cols.st(r[u].w & SER_M24, res);
-                if (!(flags & 64u)) acc = res;
-            }
-            // a guard is always the last record of its block
-            if (((r[SER_BLOCK - 1].x >> 24) & 15u) == MCB_OP_GUARD) {
-                greg = cols.ld(r[SER_BLOCK - 1].x & SER_M24);
-                if (__all_sync(warp_mask, greg == 0)) {
-                    ip += (int)(r[SER_BLOCK - 1].w & SER_M24);
+            int skip = 0;
+            if (m.x & 0x100u) {
+                const uint4 r = ctl[5 + STR_BLOCK - 1];
+                greg = stream_operand<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
+                fence_async_global();                    // everything stored so far becomes visible to later TMA reads
+                const uint32_t any = __any_sync(0xffffffffu, active && greg != 0);
+                __syncwarp();
+                if (lane == 0) {
+                    sh->votes[gidx][warp] = any;
+                    mbar_arrive(&sh->guard_bar);
+                }
+                mbar_wait(&sh->guard_bar, gph);
+                gph ^= 1u;
+                const volatile uint32_t *vt = sh->votes[gidx];
+                const uint32_t all = vt[0] | vt[1] | vt[2] | vt[3];
+                gidx ^= 1u;
+                if (!all) {
+                    skip = (int)m.y;
                     n_skipped += 1;
                 }
             }
-            ip += SER_BLOCK;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sh->empty[g]);
+            if (++g == (uint32_t)n_groups) { g = 0; ph ^= 1u; }
+            b += 1 + skip;
         }
     }
-    if (skipped && n_skipped && (threadIdx.x & 31) == __ffs(warp_mask) - 1 && blockIdx.x == 0 && (threadIdx.x >> 5) == 0)
-        atomicAdd(skipped, n_skipped);
+    if (skipped && n_skipped && blockIdx.x == 0 && tid == 0) atomicAdd(skipped, n_skipped);
 }
 
 template <typename W>
-static int launch_serial_w(const uint4 *recs, int n_recs, const View &v, long long steps,
+static int launch_stream_w(const uint32_t *stream, int n_blocks, int ring_rows, const View &v, long long steps,
                            unsigned long long *d_skipped, cudaStream_t s) {
-    const long long cols = v.n_words * (long long)(8 / sizeof(W));
-    int block = g_tune.serial_block;
-    if (block > 128) block = 128;
-    if (block < 32) block = 32;
-    block = block / 32 * 32;
-    // warps are independent: spread them over the SMs first, then stack them
-    while (block > 32 && (cols + block - 1) / block < (long long)sm_count() * 2) block /= 2;
-    const long long grid = (cols + block - 1) / block;
-    if (v.pstride * 8 >= (1ll << 32) || v.sstride * 8 >= (1ll << 32))
-        return fail(MCB_ERR_ARG, "row stride of 4 GB or more is not supported by the serial kernel");
+    const long long per_word = 8 / (long long)sizeof(W);
+    const long long cols = v.n_words * per_word;
+    const long long ext_cols = (v.n_words + 15) / 16 * 16 * per_word;         // rows are padded to 128 bytes
+    const long long grid = (cols + STR_NT - 1) / STR_NT;
+    if (grid > 0x7fffffffll) return fail(MCB_ERR_ARG, "too many lane columns for one launch");
+    if ((reinterpret_cast<uintptr_t>(v.persist) & 15) || ((v.pstride * 8) & 15) ||
+        (v.scratch_biased && ((reinterpret_cast<uintptr_t>(v.scratch_biased) & 15) || ((v.sstride * 8) & 15))))
+        return fail(MCB_ERR_ARG, "state rows must be 16-byte aligned for TMA bulk copies");
     const bool unified = v.scratch_biased == nullptr ||
                          (v.scratch_biased == v.persist && v.sstride == v.pstride);
-    if (unified) k_run_serial<W, true><<<(unsigned)grid, block, 0, s>>>(recs, n_recs, v, steps, cols, d_skipped,
-                                                                        g_tune.serial_pf_l1, g_tune.serial_rec_ahead);
-    else k_run_serial<W, false><<<(unsigned)grid, block, 0, s>>>(recs, n_recs, v, steps, cols, d_skipped,
-                                                                  g_tune.serial_pf_l1, g_tune.serial_rec_ahead);
-    LAUNCH_CHECK("k_run_serial");
+    if (ring_rows < 1) ring_rows = 1;
+    if (ring_rows > STR_RING_ROWS) ring_rows = STR_RING_ROWS;
+    const size_t row_pitch = STR_NT * sizeof(W);
+    const size_t group_bytes = STR_CTRL_PITCH + (size_t)ring_rows * row_pitch;
+    const size_t fixed = STR_HEAD_BYTES + STR_STASH * row_pitch;
+    int dev = 0, max_smem = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    long long budget = g_tune.stream_smem_kb > 0 ? (long long)g_tune.stream_smem_kb * 1024 : (long long)max_smem;
+    if (budget > max_smem) budget = max_smem;
+    int groups = (int)((budget - (long long)fixed) / (long long)group_bytes);
+    if (groups > STR_GB_MAX) groups = STR_GB_MAX;
+    if (g_tune.stream_groups > 0 && groups > g_tune.stream_groups) groups = g_tune.stream_groups;
+    if (groups < 2) return fail(MCB_ERR_ARG, "shared memory too small for the stream ring");
+    const size_t smem = fixed + (size_t)groups * group_bytes;
+    auto kern = unified ? k_run_stream<W, true> : k_run_stream<W, false>;
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)grid, 32 * (STR_CONSUMER_WARPS + 1), smem, s>>>(stream, n_blocks, v, steps, cols, ext_cols, d_skipped,
+                                                                     groups, ring_rows);
+    LAUNCH_CHECK("k_run_stream");
     return 0;
 }
 
@@ -1172,8 +1378,8 @@ int mcb_set_tuning(const char *key, int value) {
     else if (!strcmp(key, "persist_block")) p = &g_tune.persist_block;
     else if (!strcmp(key, "serial_block")) p = &g_tune.serial_block;
     else if (!strcmp(key, "serial_word_bytes")) p = &g_tune.serial_word_bytes;
-    else if (!strcmp(key, "serial_pf_l1")) p = &g_tune.serial_pf_l1;
-    else if (!strcmp(key, "serial_rec_ahead")) p = &g_tune.serial_rec_ahead;
+    else if (!strcmp(key, "stream_groups")) p = &g_tune.stream_groups;
+    else if (!strcmp(key, "stream_smem_kb")) p = &g_tune.stream_smem_kb;
     else return fail(MCB_ERR_ARG, "unknown tuning key %s", key);
     int old = *p;
     *p = value;
@@ -1310,32 +1516,28 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
     return 0;
 }
 
-int mcb_run_serial(const uint32_t *d_records, int n_records, const mcb_state *st, int64_t steps,
+int mcb_run_serial(const uint32_t *d_stream, int n_blocks, const mcb_state *st, int64_t steps,
                    int word_bytes, uint64_t *d_skipped, void *stream) {
     int rc = check_state(st);
     if (rc) return rc;
-    if (n_records < 0 || (n_records > 0 && !d_records) || steps < 0)
+    if (n_blocks < 0 || (n_blocks > 0 && !d_stream) || steps < 0)
         return fail(MCB_ERR_ARG, "bad serial-run arguments");
-    if (n_records % SER_BLOCK) return fail(MCB_ERR_ARG, "serial stream must be a multiple of %d records", SER_BLOCK);
-    if (n_records == 0 || steps == 0 || st->n_words == 0) return 0;
+    if (n_blocks == 0 || steps == 0 || st->n_words == 0) return 0;
     if (st->n_slots > (1 << 24)) return fail(MCB_ERR_ARG, "serial records address at most 2^24 slots");
+    if (reinterpret_cast<uintptr_t>(d_stream) & 15) return fail(MCB_ERR_ARG, "the stream must be 16-byte aligned");
     const View v = make_view(st);
-    const uint4 *recs = reinterpret_cast<const uint4 *>(d_records);
     cudaStream_t s = (cudaStream_t)stream;
     unsigned long long *sk = reinterpret_cast<unsigned long long *>(d_skipped);
+    int ring_rows = word_bytes >> 8;                    // optional: rows a group must hold (0: the format's maximum)
+    word_bytes &= 0xff;
     if (word_bytes == 0) word_bytes = g_tune.serial_word_bytes;
-    if (word_bytes == 0) {
-        // narrower words = more independent warps (latency hiding) but more instructions per byte:
-        // split until every SM has about 8 warps
-        const long long want = (long long)sm_count() * 256;
-        word_bytes = 8;
-        while (word_bytes > 2 && st->n_words * (8 / word_bytes) < want) word_bytes /= 2;
-    }
+    if (word_bytes == 0) word_bytes = 8;
+    if (ring_rows <= 0) ring_rows = STR_RING_ROWS;
     switch (word_bytes) {
-        case 8: return launch_serial_w<uint64_t>(recs, n_records, v, steps, sk, s);
-        case 4: return launch_serial_w<uint32_t>(recs, n_records, v, steps, sk, s);
-        case 2: return launch_serial_w<uint16_t>(recs, n_records, v, steps, sk, s);
-        case 1: return launch_serial_w<uint8_t>(recs, n_records, v, steps, sk, s);
+        case 8: return launch_stream_w<uint64_t>(d_stream, n_blocks, ring_rows, v, steps, sk, s);
+        case 4: return launch_stream_w<uint32_t>(d_stream, n_blocks, ring_rows, v, steps, sk, s);
+        case 2: return launch_stream_w<uint16_t>(d_stream, n_blocks, ring_rows, v, steps, sk, s);
+        case 1: return launch_stream_w<uint8_t>(d_stream, n_blocks, ring_rows, v, steps, sk, s);
         default: return fail(MCB_ERR_ARG, "word_bytes must be 1, 2, 4 or 8");
     }
 }

@@ -58,7 +58,7 @@ class B200Engine(Executor):
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
                  resident_word_bytes=0, in_flight=2, streams=None, level_hints=False,
                  share_edge_detectors=False, sort_level_by_fanin=False, serial_guard=True,
-                 serial_prefetch=64, serial_word_bytes=0):
+                 serial_word_bytes=0, serial_options: Optional[dict] = None):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -83,7 +83,7 @@ class B200Engine(Executor):
                 from . import serial
                 program = serial.compile_serial(design, keep=keep, observe=observe,
                                                 share_edge_detectors=share_edge_detectors,
-                                                guard=serial_guard, prefetch_distance=serial_prefetch)
+                                                guard=serial_guard, **(serial_options or {}))
             else:
                 program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges,
                                                   share_edge_detectors=share_edge_detectors,
@@ -115,13 +115,18 @@ class B200Engine(Executor):
                 (mode == "auto" and avg_level * min(self.words, DEFAULT_TILE_WORDS) >= (1 << 19)))
         if tile_words is None:
             fits = (P + S) * self.stride * 8 <= budget
-            if fits and not (wide and self.n_streams > 1 and self.words > 2 * DEFAULT_TILE_WORDS):
+            # a level launch should carry as many gate-words as a 5,000-gate level of a 512-word tile does
+            # (the measured sweet spot on C5); narrow levels (C3: 64 gates) get proportionally wider tiles
+            target = DEFAULT_TILE_WORDS
+            if avg_level < 5000:
+                target = _round_up(int(min(self.words, DEFAULT_TILE_WORDS * 5000 / max(avg_level, 1.0))), _ALIGN_WORDS)
+            if fits and not (wide and self.n_streams > 1 and self.words > 2 * target):
                 tile_words = self.words                      # everything resident, one tile
             else:
                 # wide level sweeps run best as small tiles (L2-resident levels) alternating over 2 streams
                 room = max(budget - persist_bytes, 0)
                 planes = max(self.n_streams, self.in_flight)
-                tile_words = max(_ALIGN_WORDS, min(DEFAULT_TILE_WORDS,
+                tile_words = max(_ALIGN_WORDS, min(target,
                                                    (room // max(1, S * 8 * planes)) // _ALIGN_WORDS * _ALIGN_WORDS))
         tile_words = int(min(tile_words, self.words))
         if tile_words < self.words:
@@ -297,8 +302,10 @@ class B200Engine(Executor):
         if self.mode == "serial":
             if self._skipped is None:
                 self._skipped = self.rt.zeros_words(1)
+            # a ring group only has to hold as many rows as the widest block stages
+            rows = int(getattr(self.program, "serial_info", {}).get("max_ring_rows", 0))
             self.rt.run_serial(self._d_records, len(self.program.records), self._state_for(c0, n), steps,
-                               self.serial_word_bytes, self._skipped)
+                               self.serial_word_bytes | (max(rows, 1) << 8), self._skipped)
         elif self.mode == "levels_grouped":
             d_rec, _, h_off = self._grouped()
             st = self._state_for(c0, n, plane=plane)
@@ -653,25 +660,60 @@ class B200Engine(Executor):
         return [self._slots_of(p)[1] for p in pins]
 
     # ---- checkpoint / resume -------------------------------------------------------------------------
+    def _records_crc(self):
+        return int(np.bitwise_xor.reduce(self.program.records.view(np.uint32).ravel().astype(np.uint64))) \
+            if self.program.n_ops else 0
+
     def state_dict(self):
-        """Everything that survives a step: the persistent plane (all lanes) and the step count.
-        Scratch rows are dead between steps, so they are not saved."""
-        P = self.program.n_persist
+        """Everything that survives a step: the persistent rows (all lanes), keyed by SIGNAL, and the
+        step count.  Scratch rows are dead between steps, so they are not saved.  Keyed by signal, a
+        checkpoint written by one execution mode (levels / resident / serial lay their slots out
+        differently) resumes in another engine of the same circuit."""
+        prog = self.program
+        P = prog.n_persist
         rows = self.rt.to_host_u64(self._plane[:P * self.stride]).reshape(P, self.stride)[:, :self.words]
+        n_pin = len(prog.sig_kept)
+        slots = np.asarray(prog.sig_slot[:n_pin], dtype=np.int64)
+        slots = slots.copy()
+        for sig, shadow in prog.sig_shadow.items():              # a state net kept only through its 'prev' shadow
+            if sig < n_pin and not (0 <= slots[sig] < P) and 0 <= shadow < P:
+                slots[sig] = shadow
+        sigs = np.nonzero((slots >= 0) & (slots < P))[0]
+        shared = prog.net_sig is not None and not np.array_equal(prog.net_sig, prog.design.net_sig) \
+            if prog.design is not None else False
         return {"persist": np.ascontiguousarray(rows), "steps_done": self.steps_done, "lanes": self.lanes,
-                "n_persist": P, "records_crc": int(np.bitwise_xor.reduce(self.program.records.view(np.uint32).ravel()
-                                                                         .astype(np.uint64))) if self.program.n_ops else 0}
+                "n_persist": P, "records_crc": self._records_crc(), "signals": sigs.astype(np.int64),
+                "signal_slots": slots[sigs], "n_pin_signals": n_pin, "shared_edge_detectors": bool(shared)}
 
     def load_state_dict(self, state):
-        P = self.program.n_persist
-        if state["lanes"] != self.lanes or state["n_persist"] != P:
+        prog = self.program
+        P = prog.n_persist
+        if state["lanes"] != self.lanes:
             raise ValueError("checkpoint is for another engine geometry")
-        crc = int(np.bitwise_xor.reduce(self.program.records.view(np.uint32).ravel().astype(np.uint64))) \
-            if self.program.n_ops else 0
-        if state.get("records_crc", crc) != crc:
-            raise ValueError("checkpoint is for another netlist")
         full = np.zeros((P, self.stride), dtype=np.uint64)
-        full[:, :self.words] = state["persist"]
+        if state["n_persist"] == P and state.get("records_crc") == self._records_crc():
+            full[:, :self.words] = state["persist"]              # same program: slot for slot
+        else:
+            # another program of the same circuit: move the rows signal by signal
+            n_pin = len(prog.sig_kept)
+            if "signals" not in state or state["n_pin_signals"] != n_pin:
+                raise ValueError("checkpoint is for another netlist")
+            shared = prog.net_sig is not None and prog.design is not None and \
+                not np.array_equal(prog.net_sig, prog.design.net_sig)
+            if bool(state.get("shared_edge_detectors", False)) != bool(shared):
+                raise ValueError("checkpoint and engine differ in share_edge_detectors")
+            src_slot = np.full(n_pin, -1, dtype=np.int64)
+            src_slot[state["signals"]] = state["signal_slots"]
+            mine = np.asarray(prog.sig_slot[:n_pin], dtype=np.int64)
+            need = np.nonzero((mine >= 0) & (mine < P))[0]
+            missing = need[src_slot[need] < 0]
+            if len(missing):
+                raise ValueError("checkpoint lacks %d signals this engine keeps (e.g. signal %d): it was written with "
+                                 "another keep= / observe= selection" % (len(missing), int(missing[0])))
+            full[mine[need], :self.words] = state["persist"][src_slot[need]]
+            for sig, shadow in prog.sig_shadow.items():          # 'prev' shadows hold the end-of-step value
+                if 0 <= shadow < P and sig < n_pin and src_slot[sig] >= 0:
+                    full[shadow, :self.words] = state["persist"][src_slot[sig]]
         self._plane[:P * self.stride] = self.rt.to_device(full.reshape(-1))
         self.steps_done = int(state["steps_done"])
 

@@ -140,8 +140,53 @@ def register_shift(M, width=1, n=4):
     return top
 
 
+def schematic_cases():
+    """GUI-shaped sheets (mcircuit_b200/circuits.py::gui_*) rebuilt with the REFERENCE's descriptor
+    module the way Schematic.reconstruct (diagram.py:88-119) builds them, run on the reference JIT
+    the way the GUI does (app.py:732: JIT(s, 500, True), then set_pin_state / step)."""
+    out = []
+    root = circuits.gui_circuit(D, "full_adder")
+    jit = refshim.build_jit(root, 500, True)
+    probes = ["/output_9/pin", "/output_10/pin", "/xor_4/out", "/nand_11/out"]
+    script, rows = [], []
+    for v in range(8):
+        pokes = [["/input_1/pin", v & 1], ["/input_2/pin", (v >> 1) & 1], ["/input_3/pin", (v >> 2) & 1]]
+        for p, x in pokes:
+            jit.set_pin_state(p, x)
+        jit.step()
+        script.append(pokes)
+        rows.append([jit.get_pin_state(p) for p in probes])
+    out.append({"name": "gui_full_adder", "kind": "schematic", "sheet": "full_adder", "burst_size": 500,
+                "probes": probes, "script": script, "values": rows})
+    root = circuits.gui_circuit(D, "latch_and_ring")
+    jit = refshim.build_jit(root, 500, True)
+    probes = ["/output_9/pin", "/output_10/pin", "/output_11/pin", "/not_5/out", "/not_6/out", "/not_7/out"]
+    rng = random.Random(5)
+    script, rows = [], []
+    for step in range(40):
+        pokes = []
+        if step % 5 == 0:
+            r = rng.getrandbits(2)
+            pokes = [["/input_1/pin", r & 1], ["/input_2/pin", (r >> 1) & 1 if (r & 1) == 0 else 0]]
+        for p, x in pokes:
+            jit.set_pin_state(p, x)
+        jit.step()
+        script.append(pokes)
+        rows.append([jit.get_pin_state(p) for p in probes])
+    jit.burst()
+    after = [jit.get_pin_state(p) for p in probes]
+    out.append({"name": "gui_latch_and_ring", "kind": "schematic", "sheet": "latch_and_ring", "burst_size": 500,
+                "probes": probes, "script": script, "values": rows, "after_burst": after})
+    with open(os.path.join(OUT, "schematic.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    print("schematic.json:", len(out), "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    schematic_cases()
+    if "--schematic-only" in sys.argv:
+        return
     cases = []
     # --- the reference's three examples (SURVEY section 4) ---------------------------------
     cases.append(case_trace("examples_clock", "inverter_clock", {}, ["/not/out"], 10))

@@ -157,79 +157,121 @@ class CpuRuntime:
             for _ in range(int(steps)):
                 self.eval_levels(d_records, h_level_off, 0, n_levels, st)
 
-    def run_serial(self, d_records, n_records, st, steps, word_bytes=0, d_skipped=None, warp_cols=32):
-        """The serial kernel's execution model, warp by warp (``warp_cols`` columns each): blocks
-        of 8 records, EARLY loads at block start, LATE loads in place, accumulator and guard
-        register, and a GUARD jump only when every lane of the warp has a zero enable."""
-        recs = np.asarray(d_records).astype(np.int64).reshape(-1, 4)[:n_records]
-        assert len(recs) % 8 == 0
-        M = 0xFFFFFF
+    # what the emulated producer sees: "early" = it fetches a block as soon as the kernel may (GB_MAX
+    # blocks ahead, stopped by guards) and sees only stores that a fence has published; "late" = it
+    # fetches at the last moment and sees everything.  A correct stream gives the same result in both.
+    serial_fetch_model = "early"
+    serial_cta_cols = 128
+
+    def run_serial(self, d_stream, n_blocks, st, steps, word_bytes=0, d_skipped=None):
+        """The stream kernel's execution model (csrc/mcb200.cu::k_run_stream), CTA by CTA
+        (``serial_cta_cols`` lane words each): a producer stages the ring rows of each block ahead of
+        the consumers; consumers run the records with ACC / GREG / STASH / RING / LATE operands; a guard
+        is voted on by the whole CTA."""
+        from collections import deque
+        from mcircuit_b200 import serial as S
+        lines = np.asarray(d_stream).astype(np.int64).reshape(-1, S.BLOCK_WORDS)[:n_blocks]
+        blocks = [S.decode_block(l) for l in lines]
         self._launches += 1
-        for c0 in range(0, st.n_words, warp_cols):
-            n = min(warp_cols, st.n_words - c0)
+        early = self.serial_fetch_model == "early"
+        for c0 in range(0, st.n_words, self.serial_cta_cols):
+            n = min(self.serial_cta_cols, st.n_words - c0)
             sub = _State(st.persist, st.pstride, st.pcol + c0, st.scratch, st.sstride, st.scol + c0,
                          st.n_persist, st.n_slots, n)
             acc = np.zeros(n, dtype=U64)
             greg = np.zeros(n, dtype=U64)
-            for _ in range(int(steps)):
-                ip = 0
-                while ip < len(recs):
-                    blk = recs[ip:ip + 8]
-                    pat_id, units = (blk[0][3] >> 24) & 15, blk[0][3] >> 28
-                    if pat_id == 1:          # the kernel's straight-line code for a chain of enabled registers
-                        old = [sub.read([blk[u][2] & M])[0] for u in range(units)]
-                        if ((blk[0][1] >> 27) & 7) == 1:
-                            acc = sub.read([blk[0][1] & M])[0]
-                        for u in range(units):
-                            acc = (greg & acc) | (~greg & old[u])
-                            sub.write([blk[u][2] & M], acc[None, :])
-                        ip += 8
-                        continue
-                    if pat_id == 2:          # ... and for register-pipeline stages
-                        q = [sub.read([blk[2 * u][1] & M])[0] for u in range(units)]
-                        old = [sub.read([blk[2 * u + 1][2] & M])[0] for u in range(units)]
-                        for u in range(units):
-                            acc = (greg & (acc ^ q[u])) | (~greg & old[u])
-                            sub.write([blk[2 * u + 1][2] & M], acc[None, :])
-                        ip += 8
-                        continue
-                    early = {}
-                    for u, r in enumerate(blk[:units]):
-                        kinds = ((r[1] >> 24) & 7, (r[1] >> 27) & 7, (r[2] >> 24) & 7)
-                        for k in range(3):
-                            if kinds[k] == 1:
-                                early[(u, k)] = sub.read([r[k] & M])[0]
-                    for u, r in enumerate(blk[:units]):
-                        flags = r[0] >> 24
-                        op = flags & 15
-                        if op in (0, 11):
-                            continue
-                        kinds = ((r[1] >> 24) & 7, (r[1] >> 27) & 7, (r[2] >> 24) & 7)
-                        vals = []
-                        for k in range(3):
-                            if kinds[k] == 1:
-                                vals.append(early[(u, k)])
-                            elif kinds[k] == 2:
-                                vals.append(sub.read([r[k] & M])[0])
-                            elif kinds[k] == 3:
-                                vals.append(acc)
-                            elif kinds[k] == 4:
-                                vals.append(greg)
-                            else:
-                                vals.append(np.zeros(n, dtype=U64))
-                        res = _apply(int(op | (0x80 if flags & 16 else 0)), vals[0], vals[1], vals[2])
-                        if flags & 32:
-                            sub.write([r[3] & M], res[None, :])
-                        if not flags & 64:
+            stash = np.zeros((S.STASH_N, n), dtype=U64)
+            unpublished = {}                       # slot -> value the async proxy still sees
+
+            def fetch_row(slot):
+                if early and slot in unpublished:
+                    return unpublished[slot].copy()
+                return sub.read([slot])[0].copy()
+
+            def store(slot, val):
+                if early and slot not in unpublished:
+                    unpublished[slot] = sub.read([slot])[0].copy()
+                sub.write([slot], val[None, :])
+
+            queue = deque()                        # (block index, rows) staged and not yet consumed
+            prod = {"b": 0, "step": 0, "blocked": False}
+
+            def pump():
+                while not prod["blocked"] and prod["step"] < steps and len(queue) < (S.GB_MAX if early else 1):
+                    blk = blocks[prod["b"]]
+                    queue.append((prod["b"], [fetch_row(s) for s in blk["rows"]]))
+                    if blk["guard"]:
+                        prod["blocked"] = True
+                    else:
+                        prod["b"] += 1
+                        if prod["b"] >= len(blocks):
+                            prod["b"], prod["step"] = 0, prod["step"] + 1
+
+            for step in range(int(steps)):
+                b = 0
+                while b < len(blocks):
+                    pump()
+                    qb, ring = queue.popleft()
+                    assert qb == b, "producer and consumer disagree on the block sequence"
+                    blk = blocks[b]
+                    if blk["fence"]:
+                        unpublished.clear()
+
+                    def operand(kind, field):
+                        if kind == S.K_RING:
+                            return ring[field]
+                        if kind == S.K_LATE:
+                            return sub.read([field])[0]
+                        if kind == S.K_ACC:
+                            return acc
+                        if kind == S.K_GREG:
+                            return greg
+                        if kind == S.K_STASH:
+                            return stash[field].copy()
+                        return np.zeros(n, dtype=U64)
+
+                    recs = blk["records"]
+                    if blk["pattern"] == S.PAT_MUX:          # the kernel's conventions: ring row u, store slot = fetch word u
+                        d = operand(recs[0]["kinds"][1], recs[0]["fields"][1])
+                        for u in range(blk["units"]):
+                            d = (greg & d) | (~greg & ring[u])
+                            store(blk["rows"][u], d)
+                            if blk["stash"] and recs[u]["stash_out"] >= 0:
+                                stash[recs[u]["stash_out"]] = d
+                        acc = d
+                    elif blk["pattern"] == S.PAT_XM:
+                        for u in range(blk["units"]):
+                            acc = (greg & (acc ^ ring[2 * u])) | (~greg & ring[2 * u + 1])
+                            store(blk["rows"][2 * u + 1], acc)
+                            if blk["stash"] and recs[2 * u + 1]["stash_out"] >= 0:
+                                stash[recs[2 * u + 1]["stash_out"]] = acc
+                    else:
+                        for r in recs[:blk["n_recs"]]:
+                            if r["op"] in (0, 11):
+                                continue
+                            vals = [operand(k, f) for k, f in zip(r["kinds"], r["fields"])]
+                            res = _apply(int(r["op"] | (0x80 if r["neg"] else 0)), vals[0], vals[1], vals[2])
+                            if r["store"]:
+                                store(r["out"], res)
+                            if r["stash_out"] >= 0:
+                                stash[r["stash_out"]] = res
                             acc = res
-                    last = blk[7]
-                    if ((last[0] >> 24) & 15) == 11:
-                        greg = sub.read([last[0] & M])[0].copy()
+                    skip = 0
+                    if blk["guard"]:
+                        g = recs[7]
+                        greg = operand(g["kinds"][0], g["fields"][0]).copy()
+                        unpublished.clear()                    # consumers fence before they vote
                         if not greg.any():
-                            ip += int(last[3] & M)
+                            skip = blk["span"]
                             if d_skipped is not None and c0 == 0:
                                 d_skipped[0] += U64(1)
-                    ip += 8
+                        nb = b + 1 + skip
+                        prod["blocked"] = False
+                        prod["b"] = nb
+                        if prod["b"] >= len(blocks):
+                            prod["b"], prod["step"] = 0, prod["step"] + 1
+                    b += 1 + skip
+            assert not queue or prod["step"] >= steps
 
     def eval_levels_grouped(self, d_records, h_level_off, lo, hi, st):
         recs = d_records.astype(np.int64)

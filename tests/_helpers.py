@@ -112,3 +112,21 @@ def compare_engine_to_oracle(root_builder, factory_engine, lanes, steps, probes,
             got = eng.get_pin_state(p, lanes=True)
             assert np.array_equal(got, want), (step, p, got[:4], want[:4])
     return eng, ora
+
+
+def run_schematic_case(case, factory, root=None):
+    """GUI-shaped sheet (tests/golden/schematic.json, values from the reference JIT): pokes, step, probes."""
+    if root is None:
+        root = circuits.gui_circuit(MD, case["sheet"])
+    sim = factory(root, case["burst_size"])
+    for step, (pokes, row) in enumerate(zip(case["script"], case["values"])):
+        for p, v in pokes:
+            sim.set_pin_state(p, v)
+        sim.step()
+        for p, want in zip(case["probes"], row):
+            assert sim.get_pin_state(p) == want, (case["name"], step, p)
+    if "after_burst" in case:
+        sim.burst()
+        for p, want in zip(case["probes"], case["after_burst"]):
+            assert sim.get_pin_state(p) == want, (case["name"], "burst", p)
+    return sim

@@ -1,0 +1,230 @@
+"""-m gpu: BASELINE.json configs at their NAMED sizes, and the SURVEY 8f callers on the device.
+
+Full-size runs cannot be compared word for word with a CPU oracle on every lane, so each test
+combines (i) the plain-C oracle (oracle/mcref.c) on sampled lane columns spread over the tiles and
+streams the engine really uses, fed the same counter-based stimulus, with (ii) a size-independent
+property checked on ALL lanes (the multiplier multiplies, signatures are popcounts of the rows).
+"""
+import numpy as np
+import pytest
+
+import mcircuit_b200.core.descriptors as MD
+from _helpers import golden, run_schematic_case
+from mcircuit_b200 import circuits, netlist_io
+from mcircuit_b200.engine import B200Engine
+from oracle import cref, restate
+
+pytestmark = pytest.mark.gpu
+U64 = np.uint64
+
+
+def sample_columns(eng, extra=()):
+    """Lane-word columns spread over first / middle / last tiles, both edges of a tile, every stream."""
+    tw, nt, words = eng.tile_words, eng.n_tiles, eng.words
+    picks = [0, 1, tw - 1, tw, 2 * tw - 1, (nt // 2) * tw + 7, (nt // 2 + 1) * tw + tw // 2,
+             words - tw - 1, words - 2, words - 1] + list(extra)
+    return np.array(sorted({int(c) % words for c in picks}), dtype=np.int64)
+
+
+# ---- C5 at the named size: 10^6 gates, depth 200, default tiling (512-word tiles x 2 streams, graphs + PDL) ----
+def test_c5_one_million_gates_depth_200_vs_oracle():
+    n_in = 4096
+    root = circuits.random_dag(MD, n_gates=1_000_000, depth=200, n_inputs=n_in)
+    lanes = 1 << 20                                   # 32 tiles of 512 words: 16 per stream
+    eng = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="levels")
+    assert eng.program.n_gates == 1_000_000 and eng.program.n_levels == 200
+    assert eng.tile_words == 512 and eng.n_tiles == 32 and eng.n_streams == 2
+    eng.randomize_inputs()
+    eng.step()
+    cols = sample_columns(eng)
+    assert len({int(c) // eng.tile_words % eng.n_streams for c in cols}) == 2
+    ora = cref.CRef(root, 1, True, lanes=64 * 16, threads=2)
+    full = np.zeros((n_in, ora.words), dtype=U64)
+    full[:, :len(cols)] = restate.stimulus_word(np.arange(n_in)[:, None], cols[None, :])
+    ora.set_rows(ora._base("/i0/pin"), full)
+    ora.step()
+    pins = eng.output_pins()
+    assert len(pins) == 5000
+    want = ora.rows(ora._base(pins[0]), len(pins))[:, :len(cols)]
+    got = eng.sample_planes(pins, cols)
+    assert np.array_equal(got, want)
+    # all lanes: the signature kernel's popcounts are the popcounts of the rows it summarises
+    pc, _ = eng.signature()
+    for k in range(0, 5000, 613):
+        row = eng.get_pin_planes(pins[k])[0]
+        assert int(pc[k]) == int(np.unpackbits(row.view(np.uint8)).sum()), k
+    # a second pass over the same inputs is idempotent (combinational netlist, recycled scratch rows)
+    eng.step()
+    assert np.array_equal(eng.sample_planes(pins, cols), want)
+
+
+# ---- C3 at the named size: 64x64 array multiplier, 2^24 vectors ---------------------------------------------
+def test_c3_multiplier_2_24_vectors_all_lanes():
+    torch = pytest.importorskip("torch")
+    root = circuits.array_multiplier(MD, 64)
+    lanes = 1 << 24
+    eng = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="levels")
+    eng.randomize_inputs()
+    eng.step()
+    words, stride = eng.words, eng.stride
+
+    def plane(pin):
+        s = eng._flat_slots([pin])[0]
+        return eng._plane[s * stride: s * stride + words]
+
+    # (i) ALL 2^24 lanes: bit-sliced shift-and-add product recomputed with plain torch bitwise ops
+    a = [plane("/a%d/pin" % k) for k in range(64)]
+    b = [plane("/b%d/pin" % k) for k in range(64)]
+    zero = torch.zeros_like(a[0])
+    acc = [zero.clone() for _ in range(128)]
+    for j in range(64):                               # acc += (a & b_j) << j, ripple carry, bit-sliced
+        carry = zero
+        for i in range(64):
+            pp = a[i] & b[j]
+            x = acc[i + j]
+            s = x ^ pp ^ carry
+            carry = (x & pp) | (carry & (x ^ pp))
+            acc[i + j] = s
+        k = 64 + j
+        while k < 128:
+            x = acc[k]
+            acc[k] = x ^ carry
+            carry = x & carry
+            k += 1
+    for k in range(128):
+        assert torch.equal(acc[k], plane("/p%d/pin" % k)), k
+    # (ii) the oracle's C restatement on sampled columns
+    cols = sample_columns(eng)
+    ora = cref.CRef(root, 1, True, lanes=64 * 16, threads=2)
+    ins = eng.input_pins()
+    got_in = eng.sample_planes(ins, cols)
+    for p, row in zip(ins, got_in):
+        full = np.zeros((1, ora.words), dtype=U64)
+        full[0, :len(cols)] = row
+        ora.set_planes(p, full)
+    ora.step()
+    outs = eng.output_pins()
+    got = eng.sample_planes(outs, cols)
+    for p, row in zip(outs, got):
+        assert np.array_equal(ora.planes(p)[0][:len(cols)], row), p
+    # (iii) Python integers on a few lanes
+    va = restate.unpack_lanes(got_in[:64][:, :2])
+    vb = restate.unpack_lanes(got_in[64:128][:, :2]) if ins[64].startswith("/b") else None
+    if vb is not None:
+        lo, hi = restate.unpack_lanes(got[:64][:, :2]), restate.unpack_lanes(got[64:][:, :2])
+        assert all(int(x) * int(y) == (int(h) << 64 | int(l)) for x, y, l, h in zip(va, vb, lo, hi))
+
+
+# ---- C4: long resident runs ------------------------------------------------------------------------------------
+def _c4_engine_and_oracle(lanes, cols_pick, share=True, **kw):
+    root = circuits.lfsr_pipeline(MD)
+    eng = B200Engine(root, 1, True, lanes=lanes, mode="serial", keep="ports", share_edge_detectors=share, **kw)
+    seeds = ["/l%d_q%d/out" % (n, b) for n in range(256) for b in (0, 5, 17)]
+    eng.randomize_inputs(seeds)
+    words = lanes // 64
+    cols = np.array(sorted({int(c) % words for c in cols_pick(words)}), dtype=np.int64)
+    ora = cref.CRef(root, 1, True, lanes=64 * 8 * ((len(cols) + 7) // 8))
+    for s, p in enumerate(seeds):
+        full = np.zeros((1, ora.words), dtype=U64)
+        full[0, :len(cols)] = restate.stimulus_word(s, cols)
+        ora.set_planes(p, full)
+    probes = ["/pipe_out/pin"] + ["/tap%d/pin" % n for n in range(256)]
+    return eng, ora, cols, probes
+
+
+def _c4_compare(eng, ora, cols, probes):
+    got = eng.sample_planes(probes, cols)
+    for k, p in enumerate(probes):
+        assert np.array_equal(got[k], ora.planes(p)[0][:len(cols)]), p
+
+
+def test_c4_2_16_lanes_20000_steps_vs_oracle():
+    eng, ora, cols, probes = _c4_engine_and_oracle(1 << 16, lambda w: [0, 1, w // 3, w // 2, w - 2, w - 1, 511, 512])
+    eng.rt.launch_count(reset=True)
+    eng.run(20_000)                                   # 10^4 clock cycles, ONE launch
+    assert eng.rt.launch_count() == 1
+    ora.run(20_000)
+    _c4_compare(eng, ora, cols, probes)
+    eng.run(1)                                        # and an odd step count on top (other clock phase)
+    ora.run(1)
+    _c4_compare(eng, ora, cols, probes)
+
+
+def test_c4_full_run_10e5_cycles():
+    """BASELINE.json configs[3] at its named size: 10^5 clock cycles = 2 x 10^5 steps, state resident
+    on the device, one launch, end state against the oracle's C restatement run for the same 2 x 10^5
+    steps on sampled lane words."""
+    import torch
+    eng, ora, cols, probes = _c4_engine_and_oracle(1 << 20, lambda w: [0, 1, w // 2, w // 2 + 1, w - 2, w - 1, 4097, 9000])
+    eng.rt.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    eng.run(200_000)
+    e1.record()
+    torch.cuda.synchronize()
+    assert eng.rt.launch_count() == 1
+    seconds = e0.elapsed_time(e1) * 1e-3
+    ora.run(200_000)
+    _c4_compare(eng, ora, cols, probes)
+    print("C4 full size: 2^20 lanes x 200,000 steps in %.1f s (%.3f ms/step)" % (seconds, seconds * 1e3 / 200_000))
+    assert seconds < 240.0
+
+
+# ---- SURVEY 8f callers on the device -------------------------------------------------------------------------
+@pytest.mark.parametrize("case", golden("schematic.json"), ids=lambda c: c["name"])
+@pytest.mark.parametrize("mode", ["auto", "levels", "serial"])
+def test_gpu_schematic_reconstruct_vs_reference_jit_golden(case, mode):
+    """f1: the Composite that Schematic.reconstruct (diagram.py:88-119) builds, run the way the GUI
+    runs it (app.py:732), against values the reference JIT produced."""
+    run_schematic_case(case, lambda root, bs: B200Engine(root, bs, True, mode=mode))
+
+
+@pytest.mark.parametrize("case", golden("schematic.json"), ids=lambda c: c["name"])
+def test_gpu_netlist_json_load_vs_reference_jit_golden(case, tmp_path):
+    """f2: the sheet saved in the JSON netlist format (serial.py:10-62 schema) and loaded back."""
+    path = tmp_path / "sheet.json"
+    netlist_io.save(circuits.gui_circuit(MD, case["sheet"]), path)
+    run_schematic_case(case, lambda root, bs: B200Engine(root, bs, True), root=netlist_io.load(path))
+
+
+@pytest.mark.parametrize("case", [c for c in golden("traces.json") if c["name"] in
+                                  ("examples_counter", "raw_counter_4bit", "c4_gate_level_lfsr", "fuzz_seed3")],
+                         ids=lambda c: c["name"])
+def test_gpu_netlist_json_load_traces(case, tmp_path):
+    """f2: reference-JIT traces reproduced by the engine on the JSON-saved-and-reloaded circuit."""
+    from _helpers import build, run_trace_case
+    path = tmp_path / "n.json"
+    netlist_io.save(build(case), path)
+    loaded = netlist_io.load(path)
+    sim = B200Engine(loaded, case["burst_size"], True)
+    for p, v in case["pokes"]:
+        sim.set_pin_state(p, v)
+    for step, row in enumerate(case["values"]):
+        sim.step()
+        for p, want in zip(case["probes"], row):
+            assert sim.get_pin_state(p) == want, (case["name"], step, p)
+
+
+@pytest.mark.parametrize("modes", [("serial", "serial"), ("resident", "levels"), ("levels", "serial")])
+def test_gpu_checkpoint_resume_mid_run(modes):
+    """f3: state_dict() in the middle of a run, load_state_dict() into a fresh engine (possibly another
+    execution mode), continue: bit-exact with an uninterrupted oracle run on every lane."""
+    root = circuits.lfsr_pipeline(MD, 8, 16, 40, taps=(15, 13, 12, 10))
+    lanes = 64 * 24
+    a = B200Engine(root, 1, True, lanes=lanes, mode=modes[0], keep="ports")
+    ora = cref.CRef(root, 1, True, lanes=lanes)
+    rng = np.random.default_rng(9)
+    for n in range(8):
+        v = rng.integers(0, 2, size=lanes, dtype=U64)
+        a.set_pin_state(f"/l{n}_q0/out", v)
+        ora.set_pin_state(f"/l{n}_q0/out", v)
+    a.run(37)
+    snap = a.state_dict()
+    a.run(5)                                          # the original moves on; the snapshot must not
+    b = B200Engine(root, 1, True, lanes=lanes, mode=modes[1], keep="ports")
+    b.load_state_dict(snap)
+    assert b.steps_done == 37
+    b.run(64)
+    ora.run(37 + 64)
+    for p in b.output_pins():
+        assert np.array_equal(b.get_pin_planes(p), ora.planes(p)), p

@@ -1,5 +1,5 @@
-"""-m gpu: the serial kernel (k_run_serial, K3 v2) through the C ABI against the goldens harvested
-from the reference JIT and against the oracle.  Bit-exact: integer work."""
+"""-m gpu: the streamed serial kernel (k_run_stream, K3 v3) through the C ABI against the goldens
+harvested from the reference JIT and against the oracle.  Bit-exact: integer work."""
 import numpy as np
 import pytest
 
@@ -109,47 +109,46 @@ def test_gpu_serial_c4_shape_vs_oracle(share, wb):
         assert eng.regions_skipped() == done // 2   # the clock falls every other step
 
 
-def test_gpu_serial_guard_per_warp_with_lane_dependent_enable():
-    from test_serial_cpu import test_serial_guard_is_per_warp_and_exact_with_lane_dependent_clocks as cpu_case  # noqa: F401
-    # same circuit as the CPU case, on the device: warps with idle lanes only skip, others execute
-    def build_(M):
-        top = M.Composite()
-        top.add_child("en", M.ExposedPin(M.ExposedPin.IN, 1))
-        top.add_child("clk", M.Clock())
-        top.add_child("gclk", M.Gate(M.Gate.AND, 1, 2))
-        top.connect("clk", "out", "gclk", "in0")
-        top.connect("en", "", "gclk", "in1")
-        top.add_child("d", M.ExposedPin(M.ExposedPin.IN, 1))
-        n = 48
-        for i in range(n):
-            top.add_child(f"r{i}", M.Register(1))
-            top.add_child(f"x{i}", M.Gate(M.Gate.XOR, 1, 2))
-        top.add_child("q", M.ExposedPin(M.ExposedPin.OUT, 1))
-        for i in range(n):
-            top.connect("gclk", "out", f"r{i}", "clock")
-            top.connect("d" if i == 0 else f"r{i - 1}", "" if i == 0 else "out", f"x{i}", "in0")
-            top.connect("d", "", f"x{i}", "in1")
-            top.connect(f"x{i}", "out", f"r{i}", "data")
-        top.connect(f"r{n - 1}", "out", "q", "")
-        return top
-
+def test_gpu_serial_guard_per_cta_with_lane_dependent_enable():
+    """Same circuit as the CPU case, on the device: a CTA (128 thread columns) whose lanes are all idle
+    skips the region, a mixed one and the active ones execute it; every lane matches the oracle."""
+    from test_serial_cpu import run_gated_clock_case
     for wb in (8, 4):
-        lanes = 64 * 32 * 5                                  # five warps at 8 bytes per thread
-        en = np.zeros(lanes, dtype=U64)
-        en[64 * 40:] = 1                                     # first warp idle, second mixed, the rest active
-        rng = np.random.default_rng(5)
-        root = build_(MD)
-        ora = restate.RestatedJIT(root, 1, True, lanes=lanes)
-        eng = serial_factory("ports", share_edge_detectors=True, serial_word_bytes=wb)(root, 1, lanes)
-        for sim in (ora, eng):
-            sim.set_pin_state("/en/pin", en)
-        for step in range(10):
-            d = rng.integers(0, 2, size=lanes, dtype=U64)
-            for sim in (ora, eng):
-                sim.set_pin_state("/d/pin", d)
-                sim.step()
-            assert np.array_equal(eng.get_pin_state("/q/pin", lanes=True), ora.get_pin_state("/q/pin", lanes=True)), step
-        assert eng.regions_skipped() == 10                   # warp 0 never runs the region
+        cols_per_word = 8 // wb
+        lanes = 64 * (128 // cols_per_word) * 5              # five CTAs
+        idle = 64 * (128 // cols_per_word) + 64 * 40         # CTA 0 idle, CTA 1 mixed, the rest active
+        run_gated_clock_case(lambda root, n: serial_factory("ports", share_edge_detectors=True,
+                                                            serial_word_bytes=wb)(root, 1, n), lanes, idle, 12)
+
+
+@pytest.mark.parametrize("options", [{}, {"stash": False}, {"ring": False}, {"patterns": False}])
+@pytest.mark.parametrize("wb", [8, 1])
+def test_gpu_serial_many_steps_in_one_launch(options, wb):
+    """The producer runs ahead across the end of a step: run(k) in ONE launch against the oracle, every pin,
+    every lane; with each optimisation of the stream switched off in turn."""
+    cases = [(circuits.lfsr_pipeline(MD, 5, 8, 40, taps=(7, 5, 1, 0)), True), (circuits.counter_circuit(MD), False),
+             (circuits.raw_counter(MD, 3, 2), False), (circuits.gate_level_lfsr(MD), False)]
+    for seed in (400, 401, 402, 403):
+        cases.append((circuits.random_circuit(MD, seed, n_nodes=30, primitives=(
+            "Gate", "Not", "Constant", "Clock", "Counter", "Counter", "Adder", "Register", "Register"))[0], bool(seed % 2)))
+    lanes = 64 * 150                                         # ragged over two CTAs at 8 bytes per thread
+    for root, share in cases:
+        eng = B200Engine(root, 3, True, lanes=lanes, mode="serial", keep="all", share_edge_detectors=share,
+                         serial_options=options, serial_word_bytes=wb)
+        ora = restate.RestatedJIT(root, 3, True, lanes=lanes)
+        pins = [p[0] for p in compiler.flatten(root).iter_pins()]
+        rng = np.random.default_rng(11)
+        for p in pins:
+            if p.endswith("/out") and "_q" in p:
+                v = rng.integers(0, 2, size=lanes, dtype=U64)
+                eng.set_pin_state(p, v)
+                ora.set_pin_state(p, v)
+        for chunk in (1, 2, 5, 17, 64, 301):
+            eng.run(chunk)
+            for _ in range(chunk):
+                ora.step()
+            for p in pins:
+                assert np.array_equal(eng.get_pin_state(p, lanes=True), ora.get_pin_state(p, lanes=True)), (chunk, p, options)
 
 
 def test_gpu_serial_tiled_lanes():

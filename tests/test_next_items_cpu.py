@@ -10,36 +10,23 @@ from _cpu_runtime import CpuRuntime
 from mcircuit_b200 import circuits, compiler, netlist_io, schematic, waveform
 from mcircuit_b200.engine import B200Engine
 from oracle import restate
+from _helpers import golden, run_schematic_case
 
 
 def _gui_full_adder(M=MD):
     """What the GUI would hold for a 1-bit full adder drawn with LIBRARY elements (app.py:575-589)."""
-    ein, eout = M.ExposedPin(M.ExposedPin.IN), M.ExposedPin(M.ExposedPin.OUT)
-    elements = [("input0", ein), ("input1", ein), ("input2", ein), ("xor0", M.Gate(M.Gate.XOR)),
-                ("xor1", M.Gate(M.Gate.XOR)), ("and0", M.Gate(M.Gate.AND)), ("and1", M.Gate(M.Gate.AND)),
-                ("or0", M.Gate(M.Gate.OR)), ("output0", eout), ("output1", eout), ("nand_unused", M.Gate(M.Gate.AND, negated=True))]
-    nets = [
-        [("input0", "pin"), ("xor0", "in0"), ("and1", "in0")],
-        [("input1", "pin"), ("xor0", "in1"), ("and1", "in1")],
-        [("input2", "pin"), ("xor1", "in1"), ("and0", "in1")],
-        [("xor0", "out"), ("xor1", "in0"), ("and0", "in0")],
-        [("xor1", "out"), ("output0", "pin")],
-        [("and0", "out"), ("or0", "in0")],
-        [("and1", "out"), ("or0", "in1")],
-        [("or0", "out"), ("output1", "pin")],
-    ]
-    return elements, nets
+    return circuits.gui_full_adder(M)
 
 
 def test_schematic_reconstruct_shape_and_result():
     elements, nets = _gui_full_adder()
     s = schematic.reconstruct(elements, nets)
     assert list(s.graph.nodes) == [n for n, _ in elements]          # children in element order
-    assert ("input0", "pin", "xor0", "in0") in s.connections and ("or0", "out", "output1", "pin") in s.connections
+    assert ("input_1", "pin", "xor_4", "in0") in s.connections and ("or_8", "out", "output_10", "pin") in s.connections
     assert len(s.connections) == 12
     # sources outer, dests inner: first edges come from input0 in dest order
-    assert list(s.graph.edges)[:2] == [("xor0", "input0"), ("xor0", "input1")] or \
-        list(s.graph.predecessors("input0")) == ["xor0", "and1"]
+    assert list(s.graph.edges)[:2] == [("xor_4", "input_1"), ("xor_4", "input_2")] or \
+        list(s.graph.predecessors("input_1")) == ["xor_4", "and_7"]
     # runs through the engine exactly like app.py:732 does: JIT(s, 500, True)
     eng = B200Engine(s, 500, True, runtime=CpuRuntime())
     ora = restate.RestatedJIT(s, 500, True)
@@ -47,12 +34,12 @@ def test_schematic_reconstruct_shape_and_result():
         for b in (0, 1):
             for c in (0, 1):
                 for sim in (eng, ora):
-                    sim.set_pin_state("/input0/pin", a)
-                    sim.set_pin_state("/input1/pin", b)
-                    sim.set_pin_state("/input2/pin", c)
+                    sim.set_pin_state("/input_1/pin", a)
+                    sim.set_pin_state("/input_2/pin", b)
+                    sim.set_pin_state("/input_3/pin", c)
                     sim.step()
-                assert eng.get_pin_state("/output0/pin") == ora.get_pin_state("/output0/pin") == (a ^ b ^ c)
-                assert eng.get_pin_state("/output1/pin") == ora.get_pin_state("/output1/pin") == (a + b + c) // 2
+                assert eng.get_pin_state("/output_9/pin") == ora.get_pin_state("/output_9/pin") == (a ^ b ^ c)
+                assert eng.get_pin_state("/output_10/pin") == ora.get_pin_state("/output_10/pin") == (a + b + c) // 2
 
 
 def test_schematic_matches_live_reference_connect_order(reference):
@@ -157,3 +144,38 @@ def test_checkpoint_resume():
     other = B200Engine(circuits.counter_circuit(MD), 1, True, lanes=128, runtime=CpuRuntime())
     with pytest.raises(ValueError):
         other.load_state_dict(snap)
+
+
+@pytest.mark.parametrize("case", golden("schematic.json"), ids=lambda c: c["name"])
+def test_schematic_golden_from_reference_jit(case, tmp_path):
+    """Sheets rebuilt the way Schematic.reconstruct does, against values the reference JIT produced;
+    the oracle, the engine (test double) and the engine on the JSON-saved-and-reloaded sheet."""
+    run_schematic_case(case, lambda root, bs: restate.RestatedJIT(root, bs, True))
+    run_schematic_case(case, lambda root, bs: B200Engine(root, bs, True, runtime=CpuRuntime()))
+    path = tmp_path / "sheet.json"
+    netlist_io.save(circuits.gui_circuit(MD, case["sheet"]), path)
+    run_schematic_case(case, lambda root, bs: B200Engine(root, bs, True, runtime=CpuRuntime()), root=netlist_io.load(path))
+
+
+@pytest.mark.parametrize("modes", [("levels", "serial"), ("serial", "resident"), ("resident", "serial"), ("serial", "levels")])
+@pytest.mark.parametrize("back_edges", ["auto", "latch"])
+def test_checkpoint_resume_across_execution_modes(modes, back_edges):
+    """A checkpoint is keyed by signal: written under one slot layout, resumed under another."""
+    root = circuits.lfsr_pipeline(MD, 3, 8, 6, taps=(7, 5, 1, 0))
+    a = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode=modes[0], keep="ports", back_edges=back_edges)
+    ora = restate.RestatedJIT(root, 1, True, lanes=128)
+    for n in range(3):
+        a.set_pin_state(f"/l{n}_q0/out", 1)
+        ora.set_pin_state(f"/l{n}_q0/out", 1)
+    a.run(11)
+    snap = a.state_dict()
+    b = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode=modes[1], keep="ports", back_edges=back_edges)
+    b.load_state_dict(snap)
+    b.run(20)
+    for _ in range(31):
+        ora.step()
+    for p in b.output_pins():
+        assert np.array_equal(b.get_pin_state(p, lanes=True), ora.get_pin_state(p, lanes=True)), p
+    shared = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode="serial", keep="ports", share_edge_detectors=True)
+    with pytest.raises(ValueError):
+        shared.load_state_dict(snap)

@@ -1,6 +1,7 @@
 """not-gpu: serial programs (mcircuit_b200/serial.py) executed by the numpy test double, which
-follows the serial kernel's execution model (blocks of 8, EARLY / LATE loads, accumulator, guard
-register, per-warp region skipping), checked against the oracle and the golden vectors."""
+follows the stream kernel's execution model (a producer staging ring rows up to GB_MAX blocks ahead
+and seeing only fenced stores; consumers with ACC / GREG / STASH / RING / LATE operands; CTA-wide
+guard votes), checked against the oracle and the golden vectors."""
 import numpy as np
 import pytest
 
@@ -96,38 +97,38 @@ def test_serial_lfsr_pipeline_vs_oracle(keep, share):
     assert info["acc_operands"] > 0 and info["stores_elided"] > 0
 
 
-def test_serial_guard_is_per_warp_and_exact_with_lane_dependent_clocks():
-    """The enable differs between lanes (a per-lane gated clock): warps whose lanes are all idle
-    skip, the others execute - every lane must still match the oracle."""
-    def build_(M):
-        top = M.Composite()
-        top.add_child("en", M.ExposedPin(M.ExposedPin.IN, 1))
-        top.add_child("clk", M.Clock())
-        top.add_child("gclk", M.Gate(M.Gate.AND, 1, 2))
-        top.connect("clk", "out", "gclk", "in0")
-        top.connect("en", "", "gclk", "in1")
-        top.add_child("d", M.ExposedPin(M.ExposedPin.IN, 1))
-        n = 48
-        for i in range(n):
-            top.add_child(f"r{i}", M.Register(1))
-            top.add_child(f"x{i}", M.Gate(M.Gate.XOR, 1, 2))
-        top.add_child("q", M.ExposedPin(M.ExposedPin.OUT, 1))
-        for i in range(n):
-            top.connect("gclk", "out", f"r{i}", "clock")
-            top.connect("d" if i == 0 else f"r{i - 1}", "" if i == 0 else "out", f"x{i}", "in0")
-            top.connect("d", "", f"x{i}", "in1")
-            top.connect(f"x{i}", "out", f"r{i}", "data")
-        top.connect(f"r{n - 1}", "out", "q", "")
-        return top
+def gated_clock_chain(M):
+    top = M.Composite()
+    top.add_child("en", M.ExposedPin(M.ExposedPin.IN, 1))
+    top.add_child("clk", M.Clock())
+    top.add_child("gclk", M.Gate(M.Gate.AND, 1, 2))
+    top.connect("clk", "out", "gclk", "in0")
+    top.connect("en", "", "gclk", "in1")
+    top.add_child("d", M.ExposedPin(M.ExposedPin.IN, 1))
+    n = 48
+    for i in range(n):
+        top.add_child(f"r{i}", M.Register(1))
+        top.add_child(f"x{i}", M.Gate(M.Gate.XOR, 1, 2))
+    top.add_child("q", M.ExposedPin(M.ExposedPin.OUT, 1))
+    for i in range(n):
+        top.connect("gclk", "out", f"r{i}", "clock")
+        top.connect("d" if i == 0 else f"r{i - 1}", "" if i == 0 else "out", f"x{i}", "in0")
+        top.connect("d", "", f"x{i}", "in1")
+        top.connect(f"x{i}", "out", f"r{i}", "data")
+    top.connect(f"r{n - 1}", "out", "q", "")
+    return top
 
-    lanes = 64 * 70                                      # three "warps" of 32 columns in the test double
-    en = np.zeros(lanes, dtype=np.uint64)
-    en[64 * 40:] = 1                                     # warp 0 fully idle, warp 1 mixed, warp 2 fully active
-    rng = np.random.default_rng(5)
+
+def run_gated_clock_case(make_engine, lanes, idle_lanes, expect_skips):
+    """The enable differs between lanes (a per-lane gated clock): CTAs whose lanes are all idle
+    skip, the others execute - every lane must still match the oracle."""
     from oracle import restate
-    root = build_(MD)
+    en = np.zeros(lanes, dtype=np.uint64)
+    en[idle_lanes:] = 1
+    rng = np.random.default_rng(5)
+    root = gated_clock_chain(MD)
     ora = restate.RestatedJIT(root, 1, True, lanes=lanes)
-    eng = serial_factory("ports", share_edge_detectors=True)(root, 1, lanes)
+    eng = make_engine(root, lanes)
     assert eng.program.serial_info["regions"] >= 1
     for sim in (ora, eng):
         sim.set_pin_state("/en/pin", en)
@@ -137,30 +138,112 @@ def test_serial_guard_is_per_warp_and_exact_with_lane_dependent_clocks():
             sim.set_pin_state("/d/pin", d)
             sim.step()
         assert np.array_equal(eng.get_pin_state("/q/pin", lanes=True), ora.get_pin_state("/q/pin", lanes=True)), step
-    assert eng.regions_skipped() == 12                   # warp 0 never runs the region
+    assert eng.regions_skipped() == expect_skips
+
+
+@pytest.mark.parametrize("model", ["early", "late"])
+def test_serial_guard_is_per_cta_and_exact_with_lane_dependent_clocks(model):
+    rt = CpuRuntime()
+    rt.serial_cta_cols = 32                              # three "CTAs" of 32 lane words in the test double
+    rt.serial_fetch_model = model
+    # CTA 0 fully idle (never runs the region), CTA 1 mixed, CTA 2 fully active
+    run_gated_clock_case(lambda root, lanes: B200Engine(root, 1, True, lanes=lanes, runtime=rt, mode="serial",
+                                                        keep="ports", share_edge_detectors=True),
+                         64 * 70, 64 * 40, 12)
+
+
+def check_stream_invariants(prog):
+    """The rules of serial.py's module docstring, re-derived by brute force from the encoded stream."""
+    blocks = list(serial.decode(prog.records))
+    nb = len(blocks)
+    n_slots = prog.n_persist + prog.n_scratch
+    stores = [[r["out"] for r in blk["records"] if r["store"] and r["op"] not in (0, serial.OP_GUARD)] for blk in blocks]
+    for b, blk in enumerate(blocks):
+        assert blk["n_rows"] <= serial.RING_ROWS and (blk["pattern"] or len(set(blk["rows"])) == blk["n_rows"])
+        if blk["pattern"] == serial.PAT_MUX:
+            assert all(blk["rows"][u] == blk["records"][u]["out"] for u in range(blk["units"]))
+        if blk["pattern"] == serial.PAT_XM:
+            assert all(blk["rows"][2 * u + 1] == blk["records"][2 * u + 1]["out"] for u in range(blk["units"]))
+        assert blk["fence"] == (b % serial.FENCE_PERIOD == 0)
+        stored = set()
+        for u, r in enumerate(blk["records"]):
+            if r["op"] == serial.OP_GUARD:
+                assert u == serial.BLOCK - 1 and blk["guard"] and b + 1 + blk["span"] <= nb
+            elif u == serial.BLOCK - 1:
+                assert not blk["guard"]
+            if r["op"] == 0:
+                continue
+            for kind, f in zip(r["kinds"], r["fields"]):
+                if kind == serial.K_RING:
+                    assert f < blk["n_rows"] and blk["rows"][f] not in stored, "ring row stored earlier in its block"
+                if kind == serial.K_LATE:
+                    assert f < n_slots
+                if kind == serial.K_STASH:
+                    assert f < serial.STASH_N
+            if r["store"] and r["op"] != serial.OP_GUARD:
+                assert r["out"] < n_slots
+                stored.add(r["out"])
+        # no store to a staged row between the point that publishes stores to the producer and this block
+        k = b - 1
+        scanned = 0
+        while scanned < 4 * nb + serial.GB_MAX + serial.FENCE_PERIOD:
+            kb = k % nb
+            if blocks[kb]["guard"]:
+                break                                    # a guard publishes its own block's stores too
+            for s in blk["rows"]:
+                assert s not in stores[kb], ("block %d stages slot %d that block %d stores" % (b, s, kb))
+            if blocks[kb]["fence"] and (b - k) >= serial.GB_MAX:
+                break                                    # the fence at its start published everything before kb
+            k -= 1
+            scanned += 1
 
 
 def test_serial_stream_invariants():
-    prog = serial.compile_circuit_serial(circuits.lfsr_pipeline(MD, 4, 8, 30, taps=(7, 5, 1, 0)), keep="ports",
-                                         share_edge_detectors=True)
-    recs = list(serial.decode(prog.records))
-    assert len(recs) % serial.BLOCK == 0
-    n_slots = prog.n_persist + prog.n_scratch
-    for blk in range(0, len(recs), serial.BLOCK):
-        stored = set()
-        for r in recs[blk:blk + serial.BLOCK]:
-            if r["op"] == serial.OP_GUARD:
-                assert r["pos"] % serial.BLOCK == serial.BLOCK - 1           # last of its block
-                assert r["out"] % serial.BLOCK == 0 and r["pos"] + 1 + r["out"] <= len(recs)
-                continue
-            for k, kind in enumerate(r["kinds"]):
-                if kind == serial.K_EARLY:
-                    assert r["slots"][k] not in stored, "EARLY load of a slot stored earlier in the block"
-                if kind in (serial.K_EARLY, serial.K_LATE):
-                    assert r["slots"][k] < n_slots
-            if r["store"]:
-                stored.add(r["out"])
-                assert r["out"] < n_slots
+    for share in (False, True):
+        check_stream_invariants(serial.compile_circuit_serial(
+            circuits.lfsr_pipeline(MD, 4, 8, 30, taps=(7, 5, 1, 0)), keep="ports", share_edge_detectors=share))
+    check_stream_invariants(serial.compile_circuit_serial(circuits.lfsr_pipeline(MD, 40, 16, 300), keep="ports",
+                                                          share_edge_detectors=True))
+    for seed in range(300, 310):
+        root, _ = circuits.random_circuit(MD, seed, n_nodes=40)
+        check_stream_invariants(serial.compile_circuit_serial(root))
+    check_stream_invariants(serial.compile_circuit_serial(circuits.ripple_adder(MD, 32), keep="ports"))
+    check_stream_invariants(serial.compile_circuit_serial(circuits.counter_circuit(MD)))
+
+
+@pytest.mark.parametrize("model", ["early", "late"])
+@pytest.mark.parametrize("options", [{}, {"stash": False}, {"ring": False}, {"patterns": False}, {"stash": False, "ring": False}])
+def test_serial_many_steps_in_one_launch(model, options):
+    """The producer runs ahead across the end of a step: run(k) in ONE call against the oracle stepping."""
+    from oracle import restate
+    rt = CpuRuntime()
+    rt.serial_fetch_model = model
+    cases = [(circuits.lfsr_pipeline(MD, 5, 8, 40, taps=(7, 5, 1, 0)), True), (circuits.counter_circuit(MD), False),
+             (circuits.raw_counter(MD, 3, 2), False), (circuits.gate_level_lfsr(MD), False)]
+    for seed in (400, 401, 402, 403):
+        cases.append((circuits.random_circuit(MD, seed, n_nodes=30, primitives=(
+            "Gate", "Not", "Constant", "Clock", "Counter", "Counter", "Adder", "Register", "Register"))[0], bool(seed % 2)))
+    for root, share in cases:
+        eng = B200Engine(root, 3, True, lanes=128, runtime=rt, mode="serial", keep="all", share_edge_detectors=share,
+                         serial_options=options)
+        ora = restate.RestatedJIT(root, 3, True, lanes=128)
+        d = compiler.flatten(root)
+        pins = [p[0] for p in d.iter_pins()]
+        rng = np.random.default_rng(11)
+        for p in pins:                                   # an all-zero LFSR stays zero and proves nothing
+            if p.endswith("/out") and "_q" in p:
+                v = rng.integers(0, 2, size=128, dtype=np.uint64)
+                eng.set_pin_state(p, v)
+                ora.set_pin_state(p, v)
+        compared = 0
+        for chunk in (1, 2, 5, 17, 64):
+            eng.run(chunk)
+            for _ in range(chunk):
+                ora.step()
+            for p in pins:
+                assert np.array_equal(eng.get_pin_state(p, lanes=True), ora.get_pin_state(p, lanes=True)), (chunk, p, options)
+                compared += 1
+        assert compared >= 5 * 3
 
 
 def test_compiling_one_design_twice_with_shared_edge_detectors_is_stable():
