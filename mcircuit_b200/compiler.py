@@ -500,18 +500,81 @@ def _lower_register(ops, desc, clock, data, out, prevclock, shared_rise=None):
     return rise
 
 
-def _lower_adder(ops, desc, cin, a, b, cout, sum_):
+def _prune_dead_temps(ops, start, live):
+    """Drop the micro-ops emitted since ``start`` whose results (compiler temporaries) nobody reads:
+    a textbook prefix network computes group-propagate terms that later levels never use."""
+    live = set(live)
+    keep = []
+    for i in range(len(ops.code) - 1, start - 1, -1):
+        o = ops.out[i]
+        if o in live or o < ops.first_temp:
+            keep.append(i)
+            live.update(x for x in (ops.a[i], ops.b[i], ops.c[i]) if x >= 0)
+    keep.reverse()
+    for name in ("code", "a", "b", "c", "out", "is_gate"):
+        lst = getattr(ops, name)
+        lst[start:] = [lst[i] for i in keep]
+
+
+def _prefix_sum(ops, a, b):
+    """s1 = a + b mod 2^w as a parallel-prefix (Kogge-Stone) network: depth log2(w) + 2 instead of w.
+    (g, p) = (a & b, a ^ b) per bit; groups combine as G = P_hi ? G_lo : G_hi (g and p are disjoint, so
+    the select is exact), P = P_hi & P_lo; the carry into bit i is G of bits 0..i-1."""
+    w = len(a)
+    start = len(ops.code)
+    p0 = [ops.emit(OP_XOR, ops.temp(), a[i], b[i]) for i in range(w)]
+    G = [ops.emit(OP_AND, ops.temp(), a[i], b[i]) for i in range(w - 1)]       # the top bit's carry-out is not needed
+    P = list(p0[:w - 1])
+    d = 1
+    while d < w - 1:
+        nG, nP = list(G), list(P)
+        for i in range(d, w - 1):
+            if ops.allow3:
+                nG[i] = ops.emit(OP_MUX, ops.temp(), P[i], G[i - d], G[i])
+            else:
+                t = ops.emit(OP_AND, ops.temp(), P[i], G[i - d])
+                nG[i] = ops.emit(OP_OR, ops.temp(), G[i], t)
+            nP[i] = ops.emit(OP_AND, ops.temp(), P[i], P[i - d])
+        G, P = nG, nP
+        d *= 2
+    s1 = [p0[0]] + [ops.emit(OP_XOR, ops.temp(), p0[i], G[i - 1]) for i in range(1, w)]
+    _prune_dead_temps(ops, start, s1)
+    return s1
+
+
+def _prefix_increment(ops, s1, k, dsts):
+    """s2 = s1 + k (k one bit) with the carries k & s1[0] & ... & s1[i-1] as a prefix-AND network."""
+    w = len(s1)
+    A = list(s1[:w - 1])                      # A[i] = AND of s1[0..i] after the sweep
+    d = 1
+    while d < w - 1:
+        nA = list(A)
+        for i in range(d, w - 1):
+            nA[i] = ops.emit(OP_AND, ops.temp(), A[i], A[i - d])
+        A = nA
+        d *= 2
+    s2 = [ops.emit(OP_XOR, dsts[0], s1[0], k)]
+    for i in range(1, w):
+        c = ops.emit(OP_AND, ops.temp(), A[i - 1], k)
+        s2.append(ops.emit(OP_XOR, dsts[i], s1[i], c))
+    return s2
+
+
+def _lower_adder(ops, desc, cin, a, b, cout, sum_, prefix=False):
     """sum = (a + b) + zext(cin) mod 2^w ; cout = sovf(a + b) | sovf(s1 + zext(cin))
     (simulator.py:135-147).  The reference loads a, b and cin before it stores
     anything, so when an output net is also one of this adder's inputs the results go to
-    temporaries first."""
+    temporaries first.  ``prefix``: the two carry chains as parallel-prefix networks (word-level
+    lowering of the primitive: same function, logarithmic depth)."""
     w = len(a)
     m = w - 1
     aliased = bool(set(sum_) & (set(a) | set(b) | set(cin))) or bool(
         set(cout) & (set(a) | set(b) | set(cin)))
     s1 = [0] * w
     carry = -1
-    for i in range(w):
+    if prefix and w > 2:
+        s1 = _prefix_sum(ops, a, b)
+    for i in range(w if not (prefix and w > 2) else 0):
         if i == 0:
             s1[0] = ops.emit(OP_XOR, ops.temp(), a[0], b[0])
             if w > 1:
@@ -535,7 +598,9 @@ def _lower_adder(ops, desc, cin, a, b, cout, sum_):
     # s2 = s1 + zext(cin)
     s2 = [0] * w
     k = cin[0]
-    for i in range(w):
+    if prefix and w > 2:
+        s2 = _prefix_increment(ops, s1, k, [ops.temp() if aliased else sum_[i] for i in range(w)])
+    for i in range(w if not (prefix and w > 2) else 0):
         dst = ops.temp() if aliased else sum_[i]
         knext = -1
         if i < m:
@@ -558,7 +623,7 @@ def _lower_adder(ops, desc, cin, a, b, cout, sum_):
         ops.emit(OP_OR, cout[0], ovf1, ovf2)
 
 
-def lower(design: Design, allow3: bool = True, share_edge_detectors: bool = False) -> _Ops:
+def lower(design: Design, allow3: bool = True, share_edge_detectors: bool = False, adder_prefix: bool = False) -> _Ops:
     """``share_edge_detectors``: Registers / Counters that read the same clock net in the same
     epoch (all before, or all after, the op that writes it) compute the same ``rise`` and hold
     the same ``prevclock`` for ever, so one ANDN + one BUF serve the whole group and the
@@ -633,7 +698,7 @@ def lower(design: Design, allow3: bool = True, share_edge_detectors: bool = Fals
             clocked(arg, _lower_register, p, p["data"], p["out"])
         elif tname == "Adder":
             p = pins(arg)
-            _lower_adder(ops, desc, p["cin"], p["a"], p["b"], p["cout"], p["sum"])
+            _lower_adder(ops, desc, p["cin"], p["a"], p["b"], p["cout"], p["sum"], prefix=adder_prefix)
         # ExposedPin, Constant and anything not in TRANSLATOR emit nothing (:214-221)
         if share_edge_detectors:
             for o in ops.out[n_seen:]:
@@ -691,7 +756,8 @@ class Program:
 
 def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
                    allow3: Optional[bool] = None, back_edges="auto",
-                   share_edge_detectors: bool = False, sort_level_by_fanin: bool = False) -> Program:
+                   share_edge_detectors: bool = False, sort_level_by_fanin: bool = False,
+                   adder_prefix: bool = False) -> Program:
     """Lower, levelize, allocate slots and encode.  ``keep``: 'all' retains every pin net
     (full drop-in observability); 'ports' retains only what a later step or the caller can
     still need - undriven nets (inputs, constants), state, root-level ports and
@@ -706,7 +772,7 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
     latch_slack = {"auto": 1, "order": 1 << 30, "latch": 0}[back_edges]
     if allow3 is None:
         allow3 = design.n_signals * 2 + 1024 < IN2_LIMIT
-    ops = lower(design, allow3, share_edge_detectors)
+    ops = lower(design, allow3, share_edge_detectors, adder_prefix)
     n_ops = len(ops.code)
     n_sig = ops.n_sig
     n_pin_sig = ops.first_temp
@@ -892,7 +958,7 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
         # in2 would not fit beside the opcode: redo with 2-input micro-ops only
         return compile_design(design, keep=keep, observe=observe, allow3=False, back_edges=back_edges,
                               share_edge_detectors=share_edge_detectors,
-                              sort_level_by_fanin=sort_level_by_fanin)
+                              sort_level_by_fanin=sort_level_by_fanin, adder_prefix=adder_prefix)
 
     # ---- optional: within a level, order records by the slots of their fan-in -------------------
     # Records of a level are independent, so their order is free.  Sorting by (in1 slot, in0

@@ -7,6 +7,7 @@
 // HBM-bound work: no tensor cores.  See DESIGN.md for the roofline of each kernel.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -74,6 +75,7 @@ struct Tuning {
     int persist_block = 1024;   // threads per CTA of the persistent level kernel
     int serial_block = 128;     // threads per CTA of the serial kernel (warps are independent)
     int serial_word_bytes = 0;  // bytes of a lane column per thread (0: auto, 8, 4, 2, 1)
+    int level_tma = 0;          // 1: the level kernel stages rows in shared memory with TMA bulk copies (K1t)
     int stream_groups = 0;      // ring groups of the stream kernel (0: as many as fit, at most 24)
     int stream_smem_kb = 0;     // shared memory the stream kernel may take per CTA (0: the device maximum)
 };
@@ -314,8 +316,200 @@ static void launch_level_t(const uint4 *recs, int n, const View &v, cudaStream_t
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// mbarrier / TMA helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_async_global() {
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// K1t: one level with the per-level signal state staged in shared memory by TMA bulk copies.
+// CTA = 1 producer warp + 4 consumer warps, persistent over the level's records (record i of CTA c
+// = c + i * gridDim.x).  Producer: per record, the 16-byte record goes into the stage header and
+// every fan-in row of the lane tile (<= 4 KB) is one cp.async.bulk into the stage, completion on
+// the stage's `full` mbarrier.  Consumers: 128 threads x 32 bytes cover a row; LOP3 on four words,
+// result into the stage's output buffer, fence.proxy.async, and every warp sends its own kilobyte
+// of the output row back with one cp.async.bulk shared -> global (bulk_group), so no CTA-wide
+// barrier is needed.  Six stages, two CTAs per SM: ~100 KB of rows in flight per SM without a
+// single LDG on the record -> address -> row chain that stalls K1.
+// ------------------------------------------------------------------------------------------
+#define LT_STAGES 6
+#define LT_ROW_BYTES 4096
+#define LT_HEAD_BYTES 1024
+struct LtSmem {
+    uint64_t full[LT_STAGES];
+    uint64_t empty[LT_STAGES];
+    uint4 hdr[LT_STAGES];
+};
+
+template <int PDL>
+__global__ void __launch_bounds__(160, 2)
+k_eval_level_tma(const uint4 *__restrict__ recs, int n_recs, View v, uint32_t row_bytes) {
+    extern __shared__ __align__(128) unsigned char lt_smem[];
+    LtSmem *sh = reinterpret_cast<LtSmem *>(lt_smem);
+    unsigned char *in_base = lt_smem + LT_HEAD_BYTES;
+    unsigned char *out_base = in_base + LT_STAGES * 3 * LT_ROW_BYTES;
+    if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        for (int s = 0; s < LT_STAGES; ++s) {
+            mbar_init(&sh->full[s], 1);
+            mbar_init(&sh->empty[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const int first = blockIdx.x, stride = gridDim.x;
+    if (warp == 4) {
+        // ---- producer ----
+        uint32_t s = 0, ph = 1;
+        bool waited = !PDL;
+        for (int i = first; i < n_recs; i += stride) {
+            const uint4 r = __ldg(recs + i);
+            if (!waited) {                              // the rows (not the records) depend on the previous level
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                waited = true;
+            }
+            mbar_wait(&sh->empty[s], ph);
+            if (lane == 0) {
+                const uint32_t op = r.x & 0x7fu;
+                const uint32_t arity = op == MCB_OP_NOP ? 0u : (op == MCB_OP_BUF ? 1u : (op >= MCB_OP_MUX ? 3u : 2u));
+                sh->hdr[s] = r;
+                mbar_expect_tx(&sh->full[s], arity * row_bytes);
+                unsigned char *dst = in_base + s * 3 * LT_ROW_BYTES;
+                if (arity >= 1) bulk_g2s(dst, row(v, r.y), row_bytes, &sh->full[s]);
+                if (arity >= 2) bulk_g2s(dst + LT_ROW_BYTES, row(v, r.z), row_bytes, &sh->full[s]);
+                if (arity >= 3) bulk_g2s(dst + 2 * LT_ROW_BYTES, row(v, r.x >> 8), row_bytes, &sh->full[s]);
+            }
+            if (++s == LT_STAGES) { s = 0; ph ^= 1u; }
+        }
+        if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
+        return;
+    }
+    // ---- consumers ----
+    if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");      // before the first store of this level
+    const uint32_t my = tid * 32u;
+    const bool has0 = my < row_bytes, has1 = my + 16u < row_bytes;
+    const uint32_t lo = warp * 1024u;
+    const uint32_t part = lo < row_bytes ? (row_bytes - lo < 1024u ? row_bytes - lo : 1024u) : 0u;
+    uint32_t s = 0, ph = 0;
+    for (int i = first; i < n_recs; i += stride) {
+        mbar_wait(&sh->full[s], ph);
+        const uint4 r = sh->hdr[s];
+        const uint32_t op = r.x & 0xffu, base = op & 0x7fu;
+        const unsigned char *in = in_base + s * 3 * LT_ROW_BYTES + my;
+        unsigned char *out = out_base + s * LT_ROW_BYTES;
+        if (base != MCB_OP_NOP && has0) {
+            ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(in), a1 = make_ulonglong2(0, 0);
+            ulonglong2 b0 = make_ulonglong2(0, 0), b1 = b0, c0 = b0, c1 = b0;
+            if (has1) a1 = *reinterpret_cast<const ulonglong2 *>(in + 16);
+            if (base != MCB_OP_BUF) {
+                b0 = *reinterpret_cast<const ulonglong2 *>(in + LT_ROW_BYTES);
+                if (has1) b1 = *reinterpret_cast<const ulonglong2 *>(in + LT_ROW_BYTES + 16);
+            }
+            if (base >= MCB_OP_MUX) {
+                c0 = *reinterpret_cast<const ulonglong2 *>(in + 2 * LT_ROW_BYTES);
+                if (has1) c1 = *reinterpret_cast<const ulonglong2 *>(in + 2 * LT_ROW_BYTES + 16);
+            }
+            ulonglong2 o0, o1;
+            o0.x = apply_op(op, a0.x, b0.x, c0.x);
+            o0.y = apply_op(op, a0.y, b0.y, c0.y);
+            o1.x = apply_op(op, a1.x, b1.x, c1.x);
+            o1.y = apply_op(op, a1.y, b1.y, c1.y);
+            *reinterpret_cast<ulonglong2 *>(out + my) = o0;
+            if (has1) *reinterpret_cast<ulonglong2 *>(out + my + 16) = o1;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stores above, seen by the bulk copy below
+        __syncwarp();
+        if (lane == 0) {
+            mbar_arrive(&sh->empty[s]);                 // this warp is done with the stage's fan-in rows
+            if (part && base != MCB_OP_NOP) {
+                bulk_s2g(reinterpret_cast<unsigned char *>(row(v, r.w)) + lo, out + lo, part);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                // the output buffer of this stage is written again LT_STAGES records from now
+                asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(LT_STAGES - 1) : "memory");
+            }
+        }
+        __syncwarp();
+        if (++s == LT_STAGES) { s = 0; ph ^= 1u; }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+static int launch_level_tma(const uint4 *recs, int n, const View &v, cudaStream_t s) {
+    const uint32_t row_bytes = (uint32_t)((v.n_words + 1) / 2 * 2 * 8);
+    const size_t smem = LT_HEAD_BYTES + (size_t)LT_STAGES * 4 * LT_ROW_BYTES;
+    int grid = sm_count() * 2;
+    if (grid > n) grid = n;
+    static bool attr_set[2] = {false, false};
+    const int pdl = g_tune.level_pdl ? 1 : 0;
+    if (!attr_set[pdl]) {
+        if (pdl) CUDA_TRY(cudaFuncSetAttribute(k_eval_level_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CUDA_TRY(cudaFuncSetAttribute(k_eval_level_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[pdl] = true;
+    }
+    if (pdl) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(160);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, k_eval_level_tma<1>, recs, n, v, row_bytes);
+    } else {
+        k_eval_level_tma<0><<<grid, 160, smem, s>>>(recs, n, v, row_bytes);
+    }
+    LAUNCH_CHECK("k_eval_level_tma");
+    return 0;
+}
+
 static int launch_level(const uint4 *recs, int n, const View &v, cudaStream_t s, bool hinted = false) {
     if (n <= 0) return 0;
+    // K1t: rows staged through shared memory by TMA bulk copies (tiles of up to 512 lane words: one 4 KB copy per row)
+    if (g_tune.level_tma && !hinted && v.n_words * 8 <= LT_ROW_BYTES && ((v.pstride * 8) & 15) == 0 &&
+        (!v.scratch_biased || ((v.sstride * 8) & 15) == 0) && (reinterpret_cast<uintptr_t>(v.persist) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(v.scratch_biased) & 15) == 0)
+        return launch_level_tma(recs, n, v, s);
     const int U = g_tune.level_unroll;
     // hinted records MUST go through the variant that masks bit 31 of the operands
     const int C = hinted ? 2 : (g_tune.level_cache >= 2 ? 1 : g_tune.level_cache);
@@ -523,34 +717,6 @@ static int launch_pipelined_ug(const uint4 *recs, const int *d_level_off, PipeAr
 // file of the CTA's columns fits, in shared memory for the entire run.
 // ------------------------------------------------------------------------------------------
 #define REC_CHUNK 512                      // records per staged chunk (8 KB)
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
-}
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                 :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    const uint32_t addr = smem_u32(bar);
-    uint32_t done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
-    } while (!done);
-}
-__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
-    asm volatile(
-        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-        :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
 
 // The word a thread owns is W = 8, 4, 2 or 1 bytes of a lane column: lanes never interact, so
 // a 64-lane word can be split among up to 8 threads.  Deep sequential circuits are latency
@@ -867,16 +1033,17 @@ static int launch_resident(const uint4 *recs, int n_recs, const View &v, long lo
 // the rules that decide which rows may be staged ahead of time.
 //
 // CTA = 4 consumer warps (128 columns) + 1 producer warp.  The producer walks the stream ahead of
-// the consumers: per block of 8 records it stages the block's 208-byte control line and every
-// state row the block reads (one cp.async.bulk per row segment of 128 columns, each issued by its
-// own lane) into one of `n_groups` shared-memory ring groups, completion on the group's `full`
+// the consumers: per block (up to 32 records) it stages the block's 768-byte control line
+// (cp.async.bulk) and every state row the block reads - one cp.async.bulk.tensor.2d per run of
+// 2^k consecutive slots, a [2^k rows x 128 columns] box of the state plane described by a tensor
+// map - into one of `n_groups` shared-memory ring groups, completion on the group's `full`
 // mbarrier; a group is reused when the four consumer warps have arrived on its `empty` mbarrier.
-// Consumers wait on `full`, run the records out of shared memory (operands: ring row, stash word,
-// accumulator, guard register, or - for rows the stream stored too recently to stage - an
-// ordinary load) and store results straight to global memory.  Nothing on the dependent chain
-// waits for L2 or HBM, and up to n_groups blocks of rows are in flight per SM.
+// Consumers wait on `full`, run the block's segments out of shared memory (operands: ring row,
+// stash word, accumulator, guard register, or - for rows the stream stored too recently to stage -
+// an ordinary load) and store results straight to global memory.  Nothing on the dependent chain
+// waits for L2 or HBM.
 //
-// A GUARD record (last of its block) is a CTA-wide vote: every consumer warp publishes whether any
+// A GUARD segment (last of its block) is a CTA-wide vote: every consumer warp publishes whether any
 // of its lanes has a non-zero enable, arrives on `guard_bar` and waits for the other warps; the
 // producer waits on the same barrier.  When the enable is zero everywhere, everybody jumps over the
 // region: MUX(0, d, out) -> out and out ^= 0 are the identity, so skipping is exact (event-driven
@@ -884,26 +1051,34 @@ static int launch_resident(const uint4 *recs, int n_recs, const View &v, long lo
 // the same identity.  Consumers execute fence.proxy.async.global before they vote and at the start
 // of every FENCE block, which is what makes their earlier stores visible to later TMA reads.
 // ------------------------------------------------------------------------------------------
-#define STR_BLOCK 8
-#define STR_RING_ROWS 16
-#define STR_WORDS 52                        // uint32 per control line
-#define STR_CTRL_BYTES 208
-#define STR_CTRL_PITCH 256
+#define STR_BLOCK 32
+#define STR_RING_ROWS 32
+#define STR_MAX_SEG 12
+#define STR_MAX_RUNS 16
+#define STR_W_SEG 4
+#define STR_W_RUN 16
+#define STR_W_SLOT 32
+#define STR_W_REC 64
+#define STR_WORDS 192                       // uint32 per control line
+#define STR_CTRL_BYTES 768
+#define STR_CTRL_PITCH 768
 #define STR_STASH 32
 #define STR_CONSUMER_WARPS 4
 #define STR_NT (32 * STR_CONSUMER_WARPS)    // columns per CTA
-#define STR_GB_MAX 24
-#define STR_PD 8                            // control lines the producer keeps in registers ahead of its issue point
+#define STR_GB_MAX 8
+#define STR_PD 4                            // control lines the producer keeps in registers ahead of its issue point
 #define STR_HEAD_BYTES 1024                 // barriers and votes
 #define STR_M24 0x00ffffffu
+#define STR_BOX_KINDS 6                     // boxes of 1, 2, 4, 8, 16, 32 rows
 enum { TK_NONE = 0, TK_RING = 1, TK_LATE = 2, TK_ACC = 3, TK_GREG = 4, TK_STASH = 5 };
+enum { SEG_GENERIC = 0, SEG_MUX = 1, SEG_XM = 2, SEG_GUARD = 3 };
 #define MCB_OP_GUARD 11
 
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void fence_async_global() {
-    asm volatile("fence.proxy.async.global;" ::: "memory");
+// one [rows x 128 columns] box of a state plane -> shared memory (row-major, dense)
+__device__ __forceinline__ void tma_box_g2s(void *dst, const void *tmap, int col, int row, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        :: "r"(smem_u32(dst)), "l"(tmap), "r"(col), "r"(row), "r"(smem_u32(bar)) : "memory");
 }
 
 struct StreamSmem {
@@ -926,16 +1101,13 @@ __device__ __forceinline__ W stream_operand(uint32_t kind, uint32_t field, const
     }
 }
 
-// Pattern 1, N enabled registers in a row: out = G ? d : out.  Ring row u holds the old value of
-// unit u and its slot (= the slot to store to) is fetch word u; the head takes d from wherever its
-// record says, every other stage takes the previous stage's NEW value (the reference's in-place
-// order) - pure register forwarding.  Straight-line: all shared-memory reads and address arithmetic
-// are hoisted above the dependent LOP3 chain by the compiler.
+// N enabled registers in a row: out = G ? d : out.  `rows` points at the ring row of the first unit (row u
+// holds the old value of unit u), `slots` at its slot (= the slot to store to); every stage takes the
+// previous stage's NEW value (the reference's in-place order) - pure register forwarding.  Straight-line:
+// the compiler hoists all shared-memory reads and address arithmetic above the dependent chain.
 template <typename W, bool UNIFIED, int N>
-__device__ __forceinline__ void stream_mux_chain(const uint4 *ctl, const W *rows, const W *stash, W *stash_w,
-                                                 const GlobalCols<W, UNIFIED> &cols, W &acc, W greg, bool active,
-                                                 bool has_stash) {
-    const uint32_t *slots = reinterpret_cast<const uint32_t *>(ctl + 1);
+__device__ __forceinline__ void stream_mux_chunk(const W *rows, const uint32_t *slots, const GlobalCols<W, UNIFIED> &cols,
+                                                 W &d, W greg, bool active) {
     uint32_t out[N];
     W old[N];
 #pragma unroll
@@ -943,61 +1115,37 @@ __device__ __forceinline__ void stream_mux_chain(const uint4 *ctl, const W *rows
         out[u] = slots[u];
         old[u] = rows[u * STR_NT];
     }
-    const uint4 r0 = ctl[5];
-    W d = stream_operand<W, UNIFIED>((r0.y >> 27) & 7u, r0.y & STR_M24, rows, stash, cols, acc, greg, active);
-    W val[N];
 #pragma unroll
     for (int u = 0; u < N; ++u) {
         d = (greg & d) | ((W)~greg & old[u]);
-        val[u] = d;
         if (active) cols.st(out[u], d);
-    }
-    acc = d;
-    if (has_stash) {
-#pragma unroll
-        for (int u = 0; u < N; ++u) {
-            const uint32_t so = reinterpret_cast<const uint32_t *>(ctl + 5 + u)[3] >> 24;
-            if (so) stash_w[(so - 1) * STR_NT] = val[u];
-        }
     }
 }
 
-// Pattern 2, N register-pipeline stages: x = acc ^ q; out = G ? x : out.  Ring rows 2u / 2u+1 hold q and
-// the old value of stage u; fetch word 2u+1 is the slot to store to.
+// N register-pipeline stages: x = acc ^ q; out = G ? x : out.  `q` / `old` point at the first stage's rows.
 template <typename W, bool UNIFIED, int N>
-__device__ __forceinline__ void stream_xor_mux(const uint4 *ctl, const W *rows, W *stash_w,
-                                               const GlobalCols<W, UNIFIED> &cols, W &acc, W greg, bool active,
-                                               bool has_stash) {
-    const uint32_t *slots = reinterpret_cast<const uint32_t *>(ctl + 1);
+__device__ __forceinline__ void stream_xm_chunk(const W *qrows, const W *orows, const uint32_t *slots,
+                                                const GlobalCols<W, UNIFIED> &cols, W &d, W greg, bool active) {
     uint32_t out[N];
-    W q[N], old[N], val[N];
+    W q[N], old[N];
 #pragma unroll
     for (int u = 0; u < N; ++u) {
-        out[u] = slots[2 * u + 1];
-        q[u] = rows[(2 * u) * STR_NT];
-        old[u] = rows[(2 * u + 1) * STR_NT];
+        out[u] = slots[u];
+        q[u] = qrows[u * STR_NT];
+        old[u] = orows[u * STR_NT];
     }
-    W d = acc;
 #pragma unroll
     for (int u = 0; u < N; ++u) {
         d = (greg & (d ^ q[u])) | ((W)~greg & old[u]);
-        val[u] = d;
         if (active) cols.st(out[u], d);
-    }
-    acc = d;
-    if (has_stash) {
-#pragma unroll
-        for (int u = 0; u < N; ++u) {
-            const uint32_t so = reinterpret_cast<const uint32_t *>(ctl + 6 + 2 * u)[3] >> 24;
-            if (so) stash_w[(so - 1) * STR_NT] = val[u];
-        }
     }
 }
 
 template <typename W, bool UNIFIED>
 __global__ void __launch_bounds__(32 * (STR_CONSUMER_WARPS + 1), 1)
 k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long long steps, long long n_cols,
-             long long ext_cols, unsigned long long *__restrict__ skipped, int n_groups, int ring_rows) {
+             const unsigned char *__restrict__ tmaps, unsigned long long *__restrict__ skipped, int n_groups,
+             int ring_rows) {
     extern __shared__ __align__(128) unsigned char smem[];
     StreamSmem *sh = reinterpret_cast<StreamSmem *>(smem);
     W *stash_base = reinterpret_cast<W *>(smem + STR_HEAD_BYTES);
@@ -1019,26 +1167,23 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
 
     if (warp == STR_CONSUMER_WARPS) {
         // ---------------- producer ----------------
-        long long left = ext_cols - c0;
-        const uint32_t row_bytes = (uint32_t)(left < STR_NT ? left : STR_NT) * (uint32_t)sizeof(W);
-        const char *pbase = reinterpret_cast<const char *>(v.persist) + c0 * (long long)sizeof(W);
-        const char *sbase = reinterpret_cast<const char *>(v.scratch_biased) + c0 * (long long)sizeof(W);
-        const unsigned long long pstride_b = (unsigned long long)v.pstride * 8ull, sstride_b = (unsigned long long)v.sstride * 8ull;
         uint32_t g = 0, ph = 1, gph = 0, gidx = 0;   // ph: the parity that lets the first pass through a fresh barrier
+        unsigned char *grp = groups;
         // The control words of the next STR_PD blocks live in registers (lane j holds word j of each
-        // line): a line is read once and never in L1, so without this window every block would pay an
-        // L2 round trip on the issue path.  A jump over a skipped region refills the window.
+        // line: meta and runs): a line is read once and never in L1, so without this window every block
+        // would pay an L2 round trip on the issue path.  A jump over a skipped region refills the window.
         uint32_t wq[STR_PD];
         int b = 0, pb = 0;                       // block being issued / next block to prefetch
         long long step = 0, pstep = 0;
         bool refill = true;
+        const bool my_word = lane < STR_W_SLOT;
         while (step < steps) {
             if (refill) {
                 pb = b;
                 pstep = step;
 #pragma unroll
                 for (int k = 0; k < STR_PD; ++k) {
-                    wq[k] = (pstep < steps && lane < 20) ? __ldg(stream + (size_t)pb * STR_WORDS + lane) : 0u;
+                    wq[k] = (pstep < steps && my_word) ? __ldg(stream + (size_t)pb * STR_WORDS + lane) : 0u;
                     if (++pb == n_blocks) { pb = 0; ++pstep; }
                 }
                 refill = false;
@@ -1047,23 +1192,27 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
             for (int k = 0; k < STR_PD; ++k) {
                 if (step >= steps || refill) break;
                 const uint32_t w = wq[k];
-                wq[k] = (pstep < steps && lane < 20) ? __ldg(stream + (size_t)pb * STR_WORDS + lane) : 0u;
+                wq[k] = (pstep < steps && my_word) ? __ldg(stream + (size_t)pb * STR_WORDS + lane) : 0u;
                 if (++pb == n_blocks) { pb = 0; ++pstep; }
                 const uint32_t m0 = __shfl_sync(0xffffffffu, w, 0);
-                const uint32_t n_rows = m0 & 0xffu;
-                unsigned char *grp = groups + (size_t)g * group_bytes;
+                const uint32_t n_rows = m0 & 0xffu, n_runs = m0 >> 24;
                 mbar_wait(&sh->empty[g], ph);
                 if (lane == 0) {
-                    mbar_expect_tx(&sh->full[g], STR_CTRL_BYTES + n_rows * row_bytes);
+                    mbar_expect_tx(&sh->full[g], STR_CTRL_BYTES + n_rows * row_pitch);
                     bulk_g2s(grp, stream + (size_t)b * STR_WORDS, STR_CTRL_BYTES, &sh->full[g]);
                 }
                 __syncwarp();
-                if (lane >= 4 && lane < 4 + n_rows) {
-                    const uint32_t slot = w & STR_M24;
-                    const char *src = (UNIFIED || slot < v.n_persist) ? pbase + slot * pstride_b : sbase + slot * sstride_b;
-                    bulk_g2s(grp + STR_CTRL_PITCH + (lane - 4) * row_pitch, src, row_bytes, &sh->full[g]);
+                if (lane >= STR_W_RUN && lane < STR_W_RUN + n_runs) {
+                    // 2^lg consecutive slots of one plane: one box of its tensor map
+                    uint32_t slot = w & STR_M24;
+                    const uint32_t first_row = (w >> 24) & 31u, lg = w >> 29;
+                    uint32_t plane = 0;
+                    if (!UNIFIED && slot >= v.n_persist) { plane = 1; slot -= v.n_persist; }
+                    tma_box_g2s(grp + STR_CTRL_PITCH + first_row * row_pitch,
+                                tmaps + (size_t)(plane * STR_BOX_KINDS + lg) * 128, (int)c0, (int)slot, &sh->full[g]);
                 }
-                if (++g == (uint32_t)n_groups) { g = 0; ph ^= 1u; }
+                grp += group_bytes;
+                if (++g == (uint32_t)n_groups) { g = 0; ph ^= 1u; grp = groups; }
                 int nb = b + 1;
                 if (m0 & 0x100u) {                       // guard: follow the consumers' vote
                     mbar_wait(&sh->guard_bar, gph);
@@ -1091,54 +1240,66 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
     W *stash_w = stash_base + tid;
     W acc = 0, greg = 0;
     uint32_t g = 0, ph = 0, gph = 0, gidx = 0;
+    unsigned char *grp = groups;
     unsigned long long n_skipped = 0;
     for (long long step = 0; step < steps; ++step) {
         int b = 0;
         while (b < n_blocks) {
-            unsigned char *grp = groups + (size_t)g * group_bytes;
             mbar_wait(&sh->full[g], ph);
-            const uint4 *ctl = reinterpret_cast<const uint4 *>(grp);
+            const uint32_t *ctl = reinterpret_cast<const uint32_t *>(grp);
+            const uint4 *recs = reinterpret_cast<const uint4 *>(grp + STR_W_REC * 4);
             const W *rows = reinterpret_cast<const W *>(grp + STR_CTRL_PITCH) + tid;
-            const uint4 m = ctl[0];
+            const uint4 m = *reinterpret_cast<const uint4 *>(ctl);
             if (m.x & 0x200u) fence_async_global();
-            const uint32_t pat = (m.x >> 16) & 15u, units = (m.x >> 20) & 0xffu;
-            const bool has_stash = (m.x & 0x400u) != 0;
-            if (pat == 1) {
-#define MCB_MUX_CASE(N) case N: stream_mux_chain<W, UNIFIED, N>(ctl, rows, stash, stash_w, cols, acc, greg, active, has_stash); break;
-                switch (units) {
-                    MCB_MUX_CASE(8) MCB_MUX_CASE(7) MCB_MUX_CASE(6) MCB_MUX_CASE(5)
-                    MCB_MUX_CASE(4) MCB_MUX_CASE(3) MCB_MUX_CASE(2) MCB_MUX_CASE(1)
-                    default: break;
-                }
-#undef MCB_MUX_CASE
-            } else if (pat == 2) {
-#define MCB_XM_CASE(N) case N: stream_xor_mux<W, UNIFIED, N>(ctl, rows, stash_w, cols, acc, greg, active, has_stash); break;
-                switch (units) {
-                    MCB_XM_CASE(4) MCB_XM_CASE(3) MCB_XM_CASE(2) MCB_XM_CASE(1)
-                    default: break;
-                }
-#undef MCB_XM_CASE
-            } else {
-#pragma unroll
-                for (int u = 0; u < STR_BLOCK; ++u) {
-                    if (u >= (int)m.z) continue;                                  // records worth decoding
-                    const uint4 r = ctl[5 + u];
-                    const uint32_t flags = r.x >> 24;
-                    const uint32_t op = flags & 15u;
-                    if (op == MCB_OP_NOP || op == MCB_OP_GUARD) continue;         // uniform
-                    const W a = stream_operand<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
-                    const W bb = stream_operand<W, UNIFIED>((r.y >> 27) & 7u, r.y & STR_M24, rows, stash, cols, acc, greg, active);
-                    const W c = stream_operand<W, UNIFIED>((r.z >> 24) & 7u, r.z & STR_M24, rows, stash, cols, acc, greg, active);
-                    const W res = apply_op_w<W>(op | ((flags & 16u) << 3), a, bb, c);
-                    if ((flags & 32u) && active) cols.st(r.w & STR_M24, res);
-                    const uint32_t so = r.w >> 24;
-                    if (so) stash_w[(so - 1) * STR_NT] = res;
-                    acc = res;
+            const uint32_t n_seg = (m.x >> 16) & 0xffu;
+            uint32_t guard_rec = 0;
+            for (uint32_t k = 0; k < n_seg; ++k) {
+                const uint32_t sw = ctl[STR_W_SEG + k];
+                const uint32_t kind = sw & 3u, f = (sw >> 8) & 31u, r0 = (sw >> 13) & 31u, so = (sw >> 18) & 63u;
+                int n = (int)((sw >> 2) & 63u);
+                if (kind == SEG_MUX) {
+                    W d = acc;
+                    if (!(sw & (1u << 24))) {                 // the head takes its data from somewhere else than the accumulator
+                        const uint4 rh = recs[f];
+                        d = stream_operand<W, UNIFIED>((rh.y >> 27) & 7u, rh.y & STR_M24, rows, stash, cols, acc, greg, active);
+                    }
+                    const W *rw = rows + r0 * STR_NT;
+                    const uint32_t *sl = ctl + STR_W_SLOT + r0;
+#define MCB_MUX_STEP(N) if (n >= N) { stream_mux_chunk<W, UNIFIED, N>(rw, sl, cols, d, greg, active); rw += N * STR_NT; sl += N; n -= N; }
+                    MCB_MUX_STEP(16) MCB_MUX_STEP(16) MCB_MUX_STEP(8) MCB_MUX_STEP(4) MCB_MUX_STEP(2) MCB_MUX_STEP(1)
+#undef MCB_MUX_STEP
+                    acc = d;
+                    if (so) stash_w[(so - 1) * STR_NT] = acc;      // a pattern segment ends where a value goes to the stash
+                } else if (kind == SEG_XM) {
+                    const W *qw = rows + r0 * STR_NT, *ow = qw + n * STR_NT;
+                    const uint32_t *sl = ctl + STR_W_SLOT + r0 + n;
+                    W d = acc;
+#define MCB_XM_STEP(N) if (n >= N) { stream_xm_chunk<W, UNIFIED, N>(qw, ow, sl, cols, d, greg, active); \
+                                     qw += N * STR_NT; ow += N * STR_NT; sl += N; n -= N; }
+                    MCB_XM_STEP(8) MCB_XM_STEP(8) MCB_XM_STEP(4) MCB_XM_STEP(2) MCB_XM_STEP(1)
+#undef MCB_XM_STEP
+                    acc = d;
+                    if (so) stash_w[(so - 1) * STR_NT] = acc;
+                } else if (kind == SEG_GUARD) {
+                    guard_rec = f;
+                } else {
+                    for (int u = 0; u < n; ++u) {
+                        const uint4 r = recs[f + u];
+                        const uint32_t flags = r.x >> 24;
+                        const W a = stream_operand<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
+                        const W bb = stream_operand<W, UNIFIED>((r.y >> 27) & 7u, r.y & STR_M24, rows, stash, cols, acc, greg, active);
+                        const W c = stream_operand<W, UNIFIED>((r.z >> 24) & 7u, r.z & STR_M24, rows, stash, cols, acc, greg, active);
+                        const W res = apply_op_w<W>((flags & 15u) | ((flags & 16u) << 3), a, bb, c);
+                        if ((flags & 32u) && active) cols.st(r.w & STR_M24, res);
+                        const uint32_t so = r.w >> 24;
+                        if (so) stash_w[(so - 1) * STR_NT] = res;
+                        acc = res;
+                    }
                 }
             }
             int skip = 0;
             if (m.x & 0x100u) {
-                const uint4 r = ctl[5 + STR_BLOCK - 1];
+                const uint4 r = recs[guard_rec];
                 greg = stream_operand<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
                 fence_async_global();                    // everything stored so far becomes visible to later TMA reads
                 const uint32_t any = __any_sync(0xffffffffu, active && greg != 0);
@@ -1159,16 +1320,104 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sh->empty[g]);
-            if (++g == (uint32_t)n_groups) { g = 0; ph ^= 1u; }
+            grp += group_bytes;
+            if (++g == (uint32_t)n_groups) { g = 0; ph ^= 1u; grp = groups; }
             b += 1 + skip;
         }
     }
     if (skipped && n_skipped && blockIdx.x == 0 && tid == 0) atomicAdd(skipped, n_skipped);
 }
 
+// ---- tensor maps of the state planes: [rows = slots][columns of W bytes], boxes of 2^k rows x 128 columns ----
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+static PFN_tensorMapEncodeTiled tensor_map_encoder() {
+    static PFN_tensorMapEncodeTiled fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_tensorMapEncodeTiled>(p);
+    }
+    return fn;
+}
+
+struct TmapEntry { unsigned char *d_maps; unsigned long long last_use; };
+static std::mutex g_tmap_mu;
+static std::unordered_map<std::string, TmapEntry> g_tmaps;
+static unsigned long long g_tmap_tick = 0;
+
+// 2 planes x 6 box heights, 128 bytes each, in device memory; cached per geometry
+static int stream_tensor_maps(const View &v, long long n_slots, int word_bytes, long long ext_cols, bool unified,
+                              const unsigned char **out) {
+    char key[256];
+    snprintf(key, sizeof key, "%p|%lld|%p|%lld|%u|%lld|%d|%lld", (void *)v.persist, v.pstride, (void *)v.scratch_biased,
+             v.sstride, v.n_persist, n_slots, word_bytes, ext_cols);
+    std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) {
+        it->second.last_use = ++g_tmap_tick;
+        *out = it->second.d_maps;
+        return 0;
+    }
+    PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return fail(MCB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    alignas(64) CUtensorMap maps[2 * STR_BOX_KINDS];
+    memset(maps, 0, sizeof maps);
+    const CUtensorMapDataType dt = word_bytes == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64
+                                 : word_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32
+                                 : word_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+    for (int plane = 0; plane < 2; ++plane) {
+        void *base;
+        long long rows, stride_words;
+        if (plane == 0) {
+            base = v.persist;
+            rows = unified ? n_slots : (long long)v.n_persist;
+            stride_words = v.pstride;
+        } else {
+            if (unified || !v.scratch_biased || n_slots <= (long long)v.n_persist) continue;
+            base = v.scratch_biased + (long long)v.n_persist * v.sstride;
+            rows = n_slots - (long long)v.n_persist;
+            stride_words = v.sstride;
+        }
+        if (rows < 1) rows = 1;
+        for (int lg = 0; lg < STR_BOX_KINDS; ++lg) {
+            const cuuint64_t dims[2] = {(cuuint64_t)ext_cols, (cuuint64_t)rows};
+            const cuuint64_t strides[1] = {(cuuint64_t)stride_words * 8ull};
+            const cuuint32_t box[2] = {STR_NT, 1u << lg};
+            const cuuint32_t estr[2] = {1, 1};
+            CUresult r = enc(&maps[plane * STR_BOX_KINDS + lg], dt, 2, base, dims, strides, box, estr,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS)
+                return fail(MCB_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): plane %d, %lld rows x %lld columns of %d bytes, "
+                            "row stride %lld bytes, box %d rows", (int)r, plane, rows, ext_cols, word_bytes,
+                            stride_words * 8, 1 << lg);
+        }
+    }
+    if (g_tmaps.size() >= 256) {                    // drop the least recently used half
+        std::vector<std::pair<unsigned long long, std::string>> order;
+        for (auto &kv : g_tmaps) order.push_back({kv.second.last_use, kv.first});
+        std::sort(order.begin(), order.end());
+        for (size_t i = 0; i < order.size() / 2; ++i) {
+            cudaFree(g_tmaps[order[i].second].d_maps);
+            g_tmaps.erase(order[i].second);
+        }
+    }
+    unsigned char *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof maps));
+    CUDA_TRY(cudaMemcpy(d, maps, sizeof maps, cudaMemcpyHostToDevice));
+    g_tmaps[key] = TmapEntry{d, ++g_tmap_tick};
+    *out = d;
+    return 0;
+}
+
 template <typename W>
-static int launch_stream_w(const uint32_t *stream, int n_blocks, int ring_rows, const View &v, long long steps,
-                           unsigned long long *d_skipped, cudaStream_t s) {
+static int launch_stream_w(const uint32_t *stream, int n_blocks, int ring_rows, const View &v, long long n_slots,
+                           long long steps, unsigned long long *d_skipped, cudaStream_t s) {
     const long long per_word = 8 / (long long)sizeof(W);
     const long long cols = v.n_words * per_word;
     const long long ext_cols = (v.n_words + 15) / 16 * 16 * per_word;         // rows are padded to 128 bytes
@@ -1176,11 +1425,14 @@ static int launch_stream_w(const uint32_t *stream, int n_blocks, int ring_rows, 
     if (grid > 0x7fffffffll) return fail(MCB_ERR_ARG, "too many lane columns for one launch");
     if ((reinterpret_cast<uintptr_t>(v.persist) & 15) || ((v.pstride * 8) & 15) ||
         (v.scratch_biased && ((reinterpret_cast<uintptr_t>(v.scratch_biased) & 15) || ((v.sstride * 8) & 15))))
-        return fail(MCB_ERR_ARG, "state rows must be 16-byte aligned for TMA bulk copies");
+        return fail(MCB_ERR_ARG, "state rows must be 16-byte aligned for TMA");
     const bool unified = v.scratch_biased == nullptr ||
                          (v.scratch_biased == v.persist && v.sstride == v.pstride);
     if (ring_rows < 1) ring_rows = 1;
     if (ring_rows > STR_RING_ROWS) ring_rows = STR_RING_ROWS;
+    const unsigned char *d_maps = nullptr;
+    int rc = stream_tensor_maps(v, n_slots, (int)sizeof(W), ext_cols, unified, &d_maps);
+    if (rc) return rc;
     const size_t row_pitch = STR_NT * sizeof(W);
     const size_t group_bytes = STR_CTRL_PITCH + (size_t)ring_rows * row_pitch;
     const size_t fixed = STR_HEAD_BYTES + STR_STASH * row_pitch;
@@ -1196,7 +1448,7 @@ static int launch_stream_w(const uint32_t *stream, int n_blocks, int ring_rows, 
     const size_t smem = fixed + (size_t)groups * group_bytes;
     auto kern = unified ? k_run_stream<W, true> : k_run_stream<W, false>;
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<(unsigned)grid, 32 * (STR_CONSUMER_WARPS + 1), smem, s>>>(stream, n_blocks, v, steps, cols, ext_cols, d_skipped,
+    kern<<<(unsigned)grid, 32 * (STR_CONSUMER_WARPS + 1), smem, s>>>(stream, n_blocks, v, steps, cols, d_maps, d_skipped,
                                                                      groups, ring_rows);
     LAUNCH_CHECK("k_run_stream");
     return 0;
@@ -1378,6 +1630,7 @@ int mcb_set_tuning(const char *key, int value) {
     else if (!strcmp(key, "persist_block")) p = &g_tune.persist_block;
     else if (!strcmp(key, "serial_block")) p = &g_tune.serial_block;
     else if (!strcmp(key, "serial_word_bytes")) p = &g_tune.serial_word_bytes;
+    else if (!strcmp(key, "level_tma")) p = &g_tune.level_tma;
     else if (!strcmp(key, "stream_groups")) p = &g_tune.stream_groups;
     else if (!strcmp(key, "stream_smem_kb")) p = &g_tune.stream_smem_kb;
     else return fail(MCB_ERR_ARG, "unknown tuning key %s", key);
@@ -1475,8 +1728,8 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
     {
         uint64_t h = 1469598103934665603ull;                       // FNV-1a of the level table
         for (int l = 0; l <= n_levels; ++l) { h ^= (uint64_t)(uint32_t)h_level_off[l]; h *= 1099511628211ull; }
-        const int tune[5] = {g_tune.level_block, g_tune.level_unroll, g_tune.level_ctas_per_sm, g_tune.level_cache,
-                             g_tune.level_pdl};
+        const int tune[6] = {g_tune.level_block, g_tune.level_unroll, g_tune.level_ctas_per_sm, g_tune.level_cache,
+                             g_tune.level_pdl, g_tune.level_tma};
         int dev = 0;
         cudaGetDevice(&dev);
         key.append((const char *)&d_records, sizeof(d_records));
@@ -1534,10 +1787,10 @@ int mcb_run_serial(const uint32_t *d_stream, int n_blocks, const mcb_state *st, 
     if (word_bytes == 0) word_bytes = 8;
     if (ring_rows <= 0) ring_rows = STR_RING_ROWS;
     switch (word_bytes) {
-        case 8: return launch_stream_w<uint64_t>(d_stream, n_blocks, ring_rows, v, steps, sk, s);
-        case 4: return launch_stream_w<uint32_t>(d_stream, n_blocks, ring_rows, v, steps, sk, s);
-        case 2: return launch_stream_w<uint16_t>(d_stream, n_blocks, ring_rows, v, steps, sk, s);
-        case 1: return launch_stream_w<uint8_t>(d_stream, n_blocks, ring_rows, v, steps, sk, s);
+        case 8: return launch_stream_w<uint64_t>(d_stream, n_blocks, ring_rows, v, st->n_slots, steps, sk, s);
+        case 4: return launch_stream_w<uint32_t>(d_stream, n_blocks, ring_rows, v, st->n_slots, steps, sk, s);
+        case 2: return launch_stream_w<uint16_t>(d_stream, n_blocks, ring_rows, v, st->n_slots, steps, sk, s);
+        case 1: return launch_stream_w<uint8_t>(d_stream, n_blocks, ring_rows, v, st->n_slots, steps, sk, s);
         default: return fail(MCB_ERR_ARG, "word_bytes must be 1, 2, 4 or 8");
     }
 }

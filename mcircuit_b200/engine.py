@@ -58,7 +58,7 @@ class B200Engine(Executor):
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
                  resident_word_bytes=0, in_flight=2, streams=None, level_hints=False,
                  share_edge_detectors=False, sort_level_by_fanin=False, serial_guard=True,
-                 serial_word_bytes=0, serial_options: Optional[dict] = None):
+                 serial_word_bytes=0, serial_options: Optional[dict] = None, adder_prefix=False):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
         if runtime is None:
@@ -83,11 +83,11 @@ class B200Engine(Executor):
                 from . import serial
                 program = serial.compile_serial(design, keep=keep, observe=observe,
                                                 share_edge_detectors=share_edge_detectors,
-                                                guard=serial_guard, **(serial_options or {}))
+                                                guard=serial_guard, adder_prefix=adder_prefix, **(serial_options or {}))
             else:
                 program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges,
                                                   share_edge_detectors=share_edge_detectors,
-                                                  sort_level_by_fanin=sort_level_by_fanin)
+                                                  sort_level_by_fanin=sort_level_by_fanin, adder_prefix=adder_prefix)
         if getattr(program, "serial", False):
             if mode not in ("auto", "serial"):
                 raise ValueError("a serial program runs in mode='serial' only")

@@ -9,9 +9,10 @@ reads see last step's value simply because their writer has not run yet, as in t
 What makes that fast on a B200 (``csrc/mcb200.cu::k_run_stream``):
 
   * **producer / consumer CTA** - one producer warp walks the stream ahead of four consumer warps and
-    stages, per block of 8 records, the block's control line and every state row the block reads
-    into a shared-memory ring with ``cp.async.bulk`` (TMA) + mbarriers; consumers never wait for
-    HBM/L2 on the dependent chain, and up to ``GB_MAX`` blocks of rows are in flight per SM;
+    stages, per block of up to 32 records, the block's control line and every state row the block
+    reads into a shared-memory ring: one ``cp.async.bulk`` for the control line and one
+    ``cp.async.bulk.tensor.2d`` (tensor-map TMA) per *run* of consecutive slots, completion on
+    mbarriers; consumers never wait for HBM/L2 on the dependent chain;
   * **register forwarding** - an operand that is the result of the record just before it is
     taken from the accumulator register (``ACC``), and a result all of whose readers are served
     that way (or from the stash) is never stored;
@@ -19,6 +20,10 @@ What makes that fast on a B200 (``csrc/mcb200.cu::k_run_stream``):
     ``STASH_N`` per-thread shared-memory words and read back from there (``STASH``): a row the
     stream wrote a moment ago cannot come through the ring (the producer may have fetched it before
     the store), and going back to L2 for it would put a memory round trip on the chain;
+  * **segments** - a block is a list of segments: generic records (decoded one by one), or a pattern
+    the kernel has straight-line code for: ``MUX`` = a chain of enabled registers
+    ``out = G ? d : out`` (every stage but the first takes the previous stage's NEW value - the
+    reference's in-place order), ``XM`` = register-pipeline stages ``out = G ? (acc ^ q) : out``;
   * **event skipping** - ``MUX(G, d, out) -> out`` and ``out ^= G`` are the identity in every
     lane where ``G`` is 0.  A maximal run of such records on one enable ``G`` (the shared
     ``rise`` of a clock: every ``Register`` and ``Counter``, simulator.py:100-127), together with
@@ -30,27 +35,30 @@ Which rows may come through the ring.  The producer fetches block ``b`` as soon 
 have finished block ``b - G`` (``G <= GB_MAX`` ring groups), and a consumer's ordinary stores are
 visible to TMA reads only after a ``fence.proxy.async`` - executed at the start of every
 ``FENCE_PERIOD``-th block and at every guard (where producer and consumers meet anyway).  So a row is
-``RING`` only if its last store lies before the latest such point that precedes ``b - GB_MAX``
-(or before the last guard in front of ``b``); otherwise it is ``STASH``, ``ACC`` or ``LATE`` (an
-ordinary load at the point of use, always correct for a thread's own column).
+``RING`` only if a guard lies between its last store and the read, or if that store is at least
+``RING_DISTANCE`` micro-ops back (32 per block x (GB_MAX + FENCE_PERIOD + 1) blocks); otherwise it is
+``STASH``, ``ACC`` or ``LATE`` (an ordinary load at the point of use, always correct for a thread's
+own column).
 
-Stream: one 208-byte control line per block = 52 words:
-  m0 = ring rows | flags << 8 (1 GUARD in record 7, 2 FENCE first, 4 a pattern block writes the stash) | pattern << 16 | units << 20
-  m1 = blocks to jump when the guard's enable is zero everywhere;  m2 = records worth decoding;  m3 = 0
-  f[16] = slots of the rows to stage, ring row j = f[j]
-  8 records of four words:
+Stream: one 768-byte control line per block = 192 words:
+  m0 = ring rows | flags << 8 (1 = ends in a GUARD segment, 2 = FENCE first) | segments << 16 | runs << 24
+  m1 = blocks to jump when the guard's enable is zero everywhere;  m2 = records;  m3 = 0
+  seg[12] = kind(2) | count << 2 | first record << 8 | first ring row << 13 | (stash entry + 1) << 18 | head is ACC << 24
+            (count: units of a pattern; a pattern segment ends at a unit whose result also goes to the stash)
+  run[16] = first slot | (first ring row | log2(rows) << 5) << 24     (2^k consecutive slots = one TMA box)
+  slot[32] = slot of ring row j
+  32 records of four words:
     w0 = a field | op(4) << 24 | neg << 28 | store << 29
     w1 = b field | kind_a(3) << 24 | kind_b(3) << 27
     w2 = c field | kind_c(3) << 24
     w3 = out slot | (stash entry + 1) << 24
   field = ring row (RING), slot (LATE), stash entry (STASH).
-Patterns (straight-line code in the kernel for the same records): 1 = up to 8 enabled registers
-``MUX(G, acc | x, ring[u]) -> f[u]``; 2 = up to 4 pipeline stages ``XOR(acc, ring[2u])`` +
-``MUX(G, acc, ring[2u+1]) -> f[2u+1]``; their rows are in this canonical order (a slot may be staged twice).
+Pattern segments use canonical rows: MUX unit u reads ring row ``first + u`` and stores to that row's slot;
+XM stage u of n reads rows ``first + u`` (q) and ``first + n + u`` (old value, and the slot it stores to).
 """
 from __future__ import annotations
 
-from bisect import bisect_left
+from bisect import bisect_left, bisect_right
 from typing import Dict, List, Optional, Sequence
 
 import numpy as np
@@ -61,31 +69,37 @@ from .compiler import (OP_ARITY, OP_BUF, OP_MUX, OP_NEG, OP_NOP, OP_XOR, Circuit
 
 OP_GUARD = 11
 K_NONE, K_RING, K_LATE, K_ACC, K_GREG, K_STASH = 0, 1, 2, 3, 4, 5
-BLOCK = 8
-RING_ROWS = 16             # rows one block can stage
-BLOCK_WORDS = 4 + RING_ROWS + 4 * BLOCK
-GB_MAX = 24                # ring groups (blocks in flight) the kernel uses at most
-FENCE_PERIOD = 16          # every block b with b % FENCE_PERIOD == 0 starts with fence.proxy.async
+SEG_GENERIC, SEG_MUX, SEG_XM, SEG_GUARD = 0, 1, 2, 3
+BLOCK = 32                 # records per block
+RING_ROWS = 32             # rows one block can stage
+MAX_SEG = 12
+MAX_RUNS = 16
+W_SEG, W_RUN, W_SLOT, W_REC = 4, 4 + MAX_SEG, 4 + MAX_SEG + MAX_RUNS, 4 + MAX_SEG + MAX_RUNS + RING_ROWS
+BLOCK_WORDS = W_REC + 4 * BLOCK
+GB_MAX = 8                 # ring groups (blocks in flight) the kernel uses at most
+FENCE_PERIOD = 4           # every block b with b % FENCE_PERIOD == 0 starts with fence.proxy.async
+RING_DISTANCE = BLOCK * (GB_MAX + FENCE_PERIOD + 1)
 STASH_N = 32               # per-thread shared-memory forwarding words
-STASH_WINDOW = 256         # micro-ops between a stashed result and its last reader, at most
+STASH_WINDOW = 512         # micro-ops between a stashed result and its last reader, at most
 SLOT_LIMIT = 1 << 24
 F_NEG, F_STORE = 1 << 4, 1 << 5
-M_GUARD, M_FENCE, M_STASH = 1 << 8, 1 << 9, 1 << 10
+M_GUARD, M_FENCE = 1 << 8, 1 << 9
 _COMMUTATIVE2 = (2, 3, 4)   # AND, OR, XOR
-PAT_MUX, PAT_XM = 1, 2
+PAT_MUX, PAT_XM = SEG_MUX, SEG_XM
 MIN_REGION = 32            # a guard costs a block boundary and a CTA-wide vote; shorter runs are not worth one
 
 
 def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_detectors: bool = False,
-                   guard: bool = True, patterns: bool = True, stash: bool = True, ring: bool = True) -> Program:
+                   guard: bool = True, patterns: bool = True, stash: bool = True, ring: bool = True,
+                   adder_prefix: bool = False) -> Program:
     """Lower ``design`` to a serial program.  ``keep`` / ``observe`` as in
     ``compiler.compile_design``; the result is a ``Program`` with ``serial=True`` whose
-    ``records`` are the control lines described in the module docstring (``uint32[n_blocks, 52]``).
+    ``records`` are the control lines described in the module docstring (``uint32[n_blocks, 192]``).
     ``guard`` / ``patterns`` / ``stash`` / ``ring`` switch the optimisations off one by one (tests, sweeps);
     the results are the same."""
     if keep not in ("all", "ports"):
         raise ValueError("keep must be 'all' or 'ports'")
-    ops = compiler.lower(design, True, share_edge_detectors)
+    ops = compiler.lower(design, True, share_edge_detectors, adder_prefix)
     code, A, B, C, OUT = ops.code, ops.a, ops.b, ops.c, ops.out
     n_ops = len(code)
     n_sig = ops.n_sig
@@ -209,86 +223,11 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
                     i = max(end, i + 1)
 
 
-    # ---- block patterns: runs the kernel has straight-line code for (see k_run_stream) ------------------
-    #   'M'  MUX(G, d, out) -> out, the enabled register; d = the accumulator or a row
-    #   'X'  XOR(acc, row) whose only reader is the 'M' right behind it (a register pipeline stage)
-    cls = [""] * n_ops
-    if patterns:
-        for i in range(n_ops):
-            k = region_of[i]
-            if k >= 0 and code[i] == OP_MUX and A[i] == regions[k][2] and C[i] == OUT[i] and B[i] != regions[k][2]:
-                cls[i] = "M"
-        for i in range(1, n_ops - 1):
-            k = region_of[i]
-            if (k >= 0 and code[i] == OP_XOR and cls[i + 1] == "M" and region_of[i + 1] == k and B[i + 1] == OUT[i]
-                    and next_only(i) and n_reads[OUT[i]] >= 1 and i != regions[k][0]
-                    and ((A[i] == OUT[i - 1]) != (B[i] == OUT[i - 1])) and regions[k][2] not in (A[i], B[i])):
-                cls[i] = "X"
-                cls[i + 1] = "m"                     # second half of an X-M pair
-
-    # a pattern block costs a block boundary on both sides: a lone unit is cheaper as generic records
-    i = 0
-    while i < n_ops:
-        if cls[i] in ("M", "X"):
-            kind = cls[i]
-            j, units = i, 0
-            while j < n_ops and cls[j] == kind and region_of[j] == region_of[i]:
-                j += 2 if kind == "X" else 1
-                units += 1
-            if units < 2:
-                for q in range(i, j):
-                    cls[q] = ""
-            i = j
-        else:
-            i += 1
-
-    # ---- layout: real records, GUARD at the last position of a block, NOP padding ---------------------
-    # entries: [kind, op index or guard signal, region index]
-    REC, NOPR, GUARDR = 0, 1, 2
-    layout: List[List[int]] = []
-
-    def pad_to(mod_target):
-        while len(layout) % BLOCK != mod_target:
-            layout.append([NOPR, -1, -1])
-
     region_start = {r[0]: k for k, r in enumerate(regions)}
     region_end = {r[1]: k for k, r in enumerate(regions)}
-    guard_pos: Dict[int, int] = {}
-    after_region = set()                     # ops that must not take their operand from ACC
-    run_kind, run_fill = "", 0               # pattern run being laid out, units in its current block
-    for i in range(n_ops):
-        if i in region_end:
-            pad_to(0)
-            after_region.add(i)
-            run_kind = ""
-        if i in region_start:
-            k = region_start[i]
-            pad_to(BLOCK - 1)
-            guard_pos[k] = len(layout)
-            layout.append([GUARDR, regions[k][2], k])
-            run_kind = ""
-        kind = {"M": "M", "X": "XM", "m": "XM"}.get(cls[i], "")
-        if cls[i] != "m":
-            cap = {"M": BLOCK, "XM": BLOCK // 2}.get(kind, 0)
-            if kind != run_kind or (kind and run_fill >= cap):
-                if kind or run_kind:
-                    pad_to(0)                        # pattern blocks start on a boundary and end in NOPs
-                run_kind, run_fill = kind, 0
-            run_fill += 1
-        layout.append([REC, i, region_of[i]])
-    pad_to(0)
-    n_rec = len(layout)
-    n_blocks = n_rec // BLOCK
-    op_pos = [0] * n_ops
-    for p, (kind, i, _) in enumerate(layout):
-        if kind == REC:
-            op_pos[i] = p
-    region_span = {}                         # blocks to jump: from the block after the guard's to the region's last
-    for k, (b, e, g) in enumerate(regions):
-        region_span[k] = op_pos[e - 1] // BLOCK - guard_pos[k] // BLOCK
+    after_region = set(region_end)           # ops right behind a region: the accumulator may be stale there
 
     # ---- who serves each read: ACC, GREG, STASH or memory ----------------------------------------------------
-    # reads[i] = [(operand index, signal, writer op of this step or -1)]
     writer_now = [-1] * n_sig
     served = [[None, None, None] for _ in range(n_ops)]       # K_ACC / K_GREG / ("stash", writer) / None = memory
     want_stash: Dict[int, int] = {}          # writer op -> last op that wants its result from the stash
@@ -339,7 +278,6 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
         for k, s in enumerate((A[i], B[i], C[i])[:arity]):
             if served[i][k] is None:
                 mem_reads[s] += 1
-    guard_sigs = {g for _, _, g in regions}
     for k, (b, e, g) in enumerate(regions):
         if k not in guard_reader:
             mem_reads[g] += 1
@@ -375,181 +313,345 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
     if n_persist + n_scratch + 1 >= SLOT_LIMIT:
         raise CircuitError("too many slots (%d) for a serial program (24-bit slot fields)" % (n_persist + n_scratch))
 
-    # ---- where every slot is stored (record positions), guards and fences: what the ring may carry -----------
-    stores_at: Dict[int, List[int]] = {}
-    for p, (kind, i, reg) in enumerate(layout):
-        if kind == REC and not elide[i]:
-            stores_at.setdefault(int(sig_slot[OUT[i]]), []).append(p)
-    guard_blocks = sorted(pos // BLOCK for pos in guard_pos.values())
+    # ---- which memory reads may come through the ring (decided in op space: see the module docstring) -------
+    store_ops: Dict[int, List[int]] = {}     # slot -> ops that store it
+    for i in range(n_ops):
+        if not elide[i]:
+            store_ops.setdefault(int(sig_slot[OUT[i]]), []).append(i)
+    guard_ops = sorted(region_start)         # a guard executes right in front of each of these ops
 
-    def last_store_block(slot, p):
-        """Block (possibly negative = earlier steps) of the last store to ``slot`` in front of record position p."""
-        lst = stores_at.get(slot)
+    def ring_ok(slot, i, for_guard=False):
+        """May the read of ``slot`` by op i (for_guard: by the guard in front of op i) be staged ahead?"""
+        if not ring:
+            return False
+        lst = store_ops.get(slot)
         if not lst:
-            return None
-        j = bisect_left(lst, p)
-        if j > 0:
-            return lst[j - 1] // BLOCK
-        return lst[-1] // BLOCK - n_blocks
+            return True                      # never stored by the stream: inputs, constants
+        j = bisect_left(lst, i)
+        last = lst[j - 1] if j > 0 else lst[-1] - n_ops
+        if i - last >= RING_DISTANCE:
+            return True
+        if guard_ops:                        # a guard (a fence and a rendezvous with the producer) in between
+            k = (bisect_left if for_guard else bisect_right)(guard_ops, i)
+            r = guard_ops[k - 1] if k > 0 else guard_ops[-1] - n_ops
+            if last < r:
+                return True
+        return False
 
-    def cover(b):
-        """Stores of blocks < cover(b) are visible to the producer's fetch of block b (module docstring)."""
-        t = b - GB_MAX
-        cyc = t // n_blocks
-        c = ((t - cyc * n_blocks) // FENCE_PERIOD) * FENCE_PERIOD + cyc * n_blocks
-        if guard_blocks:
-            j = bisect_left(guard_blocks, b)
-            g = guard_blocks[j - 1] if j > 0 else guard_blocks[-1] - n_blocks
-            c = max(c, g + 1)
-        return c
+    # ---- pattern units ------------------------------------------------------------------------------------
+    #   'M'  MUX(G, d, out) -> out, the enabled register (its old value comes through the ring)
+    #   'X'  XOR(acc, row) whose only reader is the 'M' right behind it ('m'): a register pipeline stage
+    cls = [""] * n_ops
+    if patterns:
+        for i in range(n_ops):
+            k = region_of[i]
+            if (k >= 0 and code[i] == OP_MUX and served[i][0] == K_GREG and C[i] == OUT[i] and served[i][2] is None
+                    and served[i][1] != K_GREG and not elide[i] and ring_ok(int(sig_slot[OUT[i]]), i)):
+                cls[i] = "M"
+        for i in range(n_ops - 1):
+            if (code[i] == OP_XOR and cls[i + 1] == "M" and region_of[i + 1] == region_of[i] and elide[i]
+                    and i not in stash_of and served[i + 1][1] == K_ACC and n_reads[OUT[i]] == 1):
+                sa, sb = served[i][0], served[i][1]
+                mem = B[i] if (sa == K_ACC and sb is None) else (A[i] if (sb == K_ACC and sa is None) else -1)
+                if mem >= 0 and ring_ok(int(sig_slot[mem]), i):
+                    cls[i] = "X"
+                    cls[i + 1] = "m"
 
-    # ---- operand kinds, ring rows per block, encoding -----------------------------------------------------------
-    stream = np.zeros((n_blocks, BLOCK_WORDS), dtype=np.uint32)
+    # ---- blocks: segments of records, ring rows, TMA runs ------------------------------------------------------
     n_acc = n_elided = n_late = n_ring = n_stash = n_greg = 0
-    rows: List[int] = []
-    row_of: Dict[int, int] = {}
-    stored_in_block: set = set()
-    for p, (kind, i, reg) in enumerate(layout):
-        b, u = divmod(p, BLOCK)
-        if u == 0:
-            rows, row_of, stored_in_block = [], {}, set()
-        base_w = 4 + RING_ROWS + 4 * u
+    n_seg_kind = {SEG_GENERIC: 0, SEG_MUX: 0, SEG_XM: 0, SEG_GUARD: 0}
+    n_units = {SEG_MUX: 0, SEG_XM: 0}
 
-        def memory_operand(slot):
-            """(kind, field) for a read of ``slot`` at record position p."""
-            nonlocal n_late, n_ring
-            ok = ring and slot not in stored_in_block
-            if ok:
-                lsb = last_store_block(slot, p)
-                ok = lsb is None or lsb < cover(b)
-            if ok and slot not in row_of and len(rows) >= RING_ROWS:
-                ok = False
-            if not ok:
-                n_late += 1
-                return K_LATE, slot
-            if slot not in row_of:
-                row_of[slot] = len(rows)
-                rows.append(slot)
-            n_ring += 1
-            return K_RING, row_of[slot]
+    def pieces(rows):
+        """Power-of-two boxes of consecutive slots (one plane) that cover ``rows`` in order: [(first row, log2)]."""
+        out, j = [], 0
+        while j < len(rows):
+            k = j + 1
+            while k < len(rows) and rows[k] == rows[k - 1] + 1 and (rows[k] < n_persist) == (rows[j] < n_persist):
+                k += 1
+            n = k - j
+            while n:
+                lg = n.bit_length() - 1
+                out.append((j, lg))
+                j += 1 << lg
+                n -= 1 << lg
+        return out
 
-        if kind == GUARDR:
-            g, k = i, reg
-            if k in guard_reader:
-                ak, af = K_STASH, stash_of[guard_reader[k]]
-                n_stash += 1
+    class Blk:
+        def __init__(self):
+            self.recs: List[List[int]] = []          # four words each
+            self.segs: List[List[int]] = []          # [kind, count, first record, first row]
+            self.rows: List[int] = []
+            self.row_of: Dict[int, int] = {}         # generic rows, shared between records
+            self.stored: set = set()
+            self.guard = -1                          # region whose guard ends the block
+            self.first_op = -1
+            self.sealed = False                      # the last pattern segment ended in a stash write: do not extend it
+
+        def fits(self, n_recs, new_rows, new_seg):
+            return self.fits_rows(n_recs, self.rows + new_rows, new_seg)
+
+        def fits_rows(self, n_recs, rows, new_seg):
+            if len(self.recs) + n_recs > BLOCK or len(rows) > RING_ROWS:
+                return False
+            if new_seg and len(self.segs) >= MAX_SEG:
+                return False
+            return len(pieces(rows)) <= MAX_RUNS
+
+    blocks: List[Blk] = []
+    cur = Blk()
+    guard_block: Dict[int, int] = {}
+    region_first_block: Dict[int, int] = {}
+    block_of_op = [0] * n_ops
+
+    def close():
+        nonlocal cur
+        if cur.recs:
+            blocks.append(cur)
+            cur = Blk()
+
+    def operand_plan(i, for_guard_slot=None):
+        """[(kind, field-or-slot, is_memory)] for op i's operands given the current block (nothing is added yet)."""
+        plan = []
+        if for_guard_slot is not None:
+            srcs = [for_guard_slot]
+        else:
+            arity = OP_ARITY[code[i] & 0x7F]
+            srcs = (A[i], B[i], C[i])[:arity]
+        for k, s in enumerate(srcs):
+            sv = None if for_guard_slot is not None else served[i][k]
+            if sv == K_GREG:
+                plan.append([K_GREG, 0])
+            elif sv == K_ACC:
+                plan.append([K_ACC, 0])
+            elif isinstance(sv, tuple):
+                plan.append([K_STASH, stash_of[sv[1]]])
             else:
-                ak, af = memory_operand(int(sig_slot[g]))
-            stream[b, base_w] = af | (OP_GUARD << 24)
-            stream[b, base_w + 1] = ak << 24
-            stream[b, 0] |= M_GUARD
-            stream[b, 1] = region_span[k]
-        elif kind == REC:
-            op = code[i]
-            base = op & 0x7F
-            arity = OP_ARITY[base]
-            kinds, fields = [K_NONE] * 3, [0] * 3
-            for k, s in enumerate((A[i], B[i], C[i])[:arity]):
-                sv = served[i][k]
-                if sv == K_GREG:
-                    kinds[k] = K_GREG
-                    n_greg += 1
-                elif sv == K_ACC:
-                    kinds[k] = K_ACC
-                    n_acc += 1
-                elif isinstance(sv, tuple):
-                    kinds[k], fields[k] = K_STASH, stash_of[sv[1]]
-                    n_stash += 1
+                slot = int(s) if for_guard_slot is not None else int(sig_slot[s])
+                if slot < 0:
+                    raise AssertionError("operand without a slot at op %d" % i)
+                if slot not in cur.stored and ring_ok(slot, i, for_guard_slot is not None):
+                    plan.append([K_RING, slot])
                 else:
-                    slot = int(sig_slot[s])
-                    if slot < 0:
-                        raise AssertionError("operand without a slot at op %d" % i)
-                    kinds[k], fields[k] = memory_operand(slot)
-            if base in _COMMUTATIVE2 and kinds[1] == K_ACC and kinds[0] != K_ACC:
-                kinds[0], kinds[1] = kinds[1], kinds[0]          # the accumulator operand goes first
-                fields[0], fields[1] = fields[1], fields[0]
-            flags = base | (F_NEG if op & OP_NEG else 0)
-            out_slot = 0
-            if not elide[i]:
-                out_slot = int(sig_slot[OUT[i]])
-                flags |= F_STORE
-                stored_in_block.add(out_slot)
+                    plan.append([K_LATE, slot])
+        return plan
+
+    def new_generic_rows(plan):
+        rows = []
+        for kind, f in plan:
+            if kind == K_RING and f not in cur.row_of and f not in rows:
+                rows.append(f)
+        return rows
+
+    def add_record(i, plan, seg_kind, new_seg):
+        """Encode op i with the operand plan (RING entries still carry slots: resolved to rows here)."""
+        nonlocal n_acc, n_elided, n_late, n_ring, n_stash, n_greg
+        kinds, fields = [K_NONE] * 3, [0] * 3
+        for k, (kind, f) in enumerate(plan):
+            kinds[k] = kind
+            if kind == K_RING:
+                if seg_kind == SEG_GENERIC or f not in pattern_row:
+                    if f not in cur.row_of:
+                        cur.row_of[f] = len(cur.rows)
+                        cur.rows.append(f)
+                    fields[k] = cur.row_of[f]
+                else:
+                    fields[k] = pattern_row[f]
+                n_ring += 1
             else:
-                n_elided += 1
-            stash_out = stash_of[i] + 1 if i in stash_of else 0
-            stream[b, base_w] = fields[0] | (flags << 24)
-            stream[b, base_w + 1] = fields[1] | ((kinds[0] | (kinds[1] << 3)) << 24)
-            stream[b, base_w + 2] = fields[2] | (kinds[2] << 24)
-            stream[b, base_w + 3] = out_slot | (stash_out << 24)
-        if u == BLOCK - 1:
-            stream[b, 0] |= len(rows)
-            stream[b, 4:4 + len(rows)] = rows
-            if b % FENCE_PERIOD == 0:
-                stream[b, 0] |= M_FENCE
+                fields[k] = f
+                n_late += kind == K_LATE
+                n_acc += kind == K_ACC
+                n_stash += kind == K_STASH
+                n_greg += kind == K_GREG
+        op = code[i]
+        base = op & 0x7F
+        if seg_kind == SEG_GENERIC and base in _COMMUTATIVE2 and kinds[1] == K_ACC and kinds[0] != K_ACC:
+            kinds[0], kinds[1] = kinds[1], kinds[0]          # the accumulator operand goes first
+            fields[0], fields[1] = fields[1], fields[0]
+        flags = base | (F_NEG if op & OP_NEG else 0)
+        out_slot = 0
+        if not elide[i]:
+            out_slot = int(sig_slot[OUT[i]])
+            flags |= F_STORE
+            cur.stored.add(out_slot)
+        else:
+            n_elided += 1
+        stash_out = stash_of[i] + 1 if i in stash_of else 0
+        if cur.first_op < 0:
+            cur.first_op = i
+        block_of_op[i] = len(blocks)
+        cur.recs.append([fields[0] | (flags << 24), fields[1] | ((kinds[0] | (kinds[1] << 3)) << 24),
+                         fields[2] | (kinds[2] << 24), out_slot | (stash_out << 24)])
 
-    # ---- tag the blocks that match a pattern exactly (the hint only selects straight-line code for the
-    # same records; a block that misses any precondition simply stays generic) ---------------------------
-    n_pat = {PAT_MUX: 0, PAT_XM: 0}
-    M24 = 0xFFFFFF
-    for b in range(n_blocks):
-        blk = [[int(x) for x in stream[b, 4 + RING_ROWS + 4 * u: 8 + RING_ROWS + 4 * u]] for u in range(BLOCK)]
-        ops_ = [(w[0] >> 24) & 15 for w in blk]
-        last = max([q + 1 for q in range(BLOCK) if ops_[q] != OP_NOP] or [0])
-        stream[b, 2] = last
-        n = 0
-        while n < BLOCK and ops_[n] not in (OP_NOP, OP_GUARD):
-            n += 1
-        if not patterns or n == 0 or any(o != OP_NOP for o in ops_[n:]):
+    pattern_row: Dict[int, int] = {}
+    i = 0
+    while i < n_ops:
+        if i in region_end:
+            close()                                          # a jump lands on a block boundary
+        if i in region_start:
+            k = region_start[i]
+            g_sig = regions[k][2]
+            for attempt in (0, 1):
+                if k in guard_reader:
+                    plan = [[K_STASH, stash_of[guard_reader[k]]]]
+                else:
+                    plan = operand_plan(i, for_guard_slot=int(sig_slot[g_sig]))
+                rows = new_generic_rows(plan)
+                if cur.fits(1, rows, True):
+                    break
+                close()
+            kind, f = plan[0]
+            if kind == K_RING:
+                if f not in cur.row_of:
+                    cur.row_of[f] = len(cur.rows)
+                    cur.rows.append(f)
+                f = cur.row_of[f]
+                n_ring += 1
+            elif kind == K_LATE:
+                n_late += 1
+            else:
+                n_stash += 1
+            cur.segs.append([SEG_GUARD, 1, len(cur.recs), 0, 0])
+            cur.recs.append([f | (OP_GUARD << 24), kind << 24, 0, 0])
+            cur.guard = k
+            n_seg_kind[SEG_GUARD] += 1
+            if cur.first_op < 0:
+                cur.first_op = i
+            guard_block[k] = len(blocks)
+            close()
+            region_first_block[k] = len(blocks)
+        c = cls[i]
+        if c == "M":
+            # one unit: 1 record, its old row; a head may bring a row of its own for d
+            for attempt in (0, 1):
+                plan = operand_plan(i)
+                last_seg = cur.segs[-1] if cur.segs else None
+                extend = (last_seg is not None and last_seg[0] == SEG_MUX and plan[1][0] == K_ACC and not cur.sealed and
+                          last_seg[2] + last_seg[1] == len(cur.recs) and last_seg[3] + last_seg[1] == len(cur.rows))
+                old_slot = int(sig_slot[OUT[i]])
+                head_rows = [] if extend else new_generic_rows([plan[1]])
+                if cur.fits(1, head_rows + [old_slot], not extend):
+                    break
+                close()
+            pattern_row = {}
+            if not extend:
+                for f in head_rows:                          # the head's own data row goes in front of the segment
+                    cur.row_of[f] = len(cur.rows)
+                    cur.rows.append(f)
+                cur.segs.append([SEG_MUX, 0, len(cur.recs), len(cur.rows), 0])
+                cur.sealed = False
+                n_seg_kind[SEG_MUX] += 1
+            seg = cur.segs[-1]
+            pattern_row = {old_slot: len(cur.rows)}
+            cur.rows.append(old_slot)
+            plan[2] = [K_RING, old_slot]
+            if plan[1][0] == K_RING and plan[1][1] == old_slot:
+                plan[1] = [K_LATE, old_slot]                 # MUX(G, out, out): degenerate, keep it simple
+            add_record(i, [plan[0], plan[1], plan[2]], SEG_MUX, False)
+            seg[1] += 1
+            if i in stash_of:                                # the segment's last value goes to the stash: it ends here
+                seg[4] = stash_of[i] + 1
+                cur.sealed = True
+            n_units[SEG_MUX] += 1
+            i += 1
             continue
+        if c == "X":
+            for attempt in (0, 1):
+                px, pm = operand_plan(i), operand_plan(i + 1)
+                last_seg = cur.segs[-1] if cur.segs else None
+                extend = (last_seg is not None and last_seg[0] == SEG_XM and not cur.sealed and
+                          last_seg[2] + 2 * last_seg[1] == len(cur.recs) and last_seg[3] + 2 * last_seg[1] == len(cur.rows))
+                q_idx = 1 if px[0][0] == K_ACC else 0
+                q_slot, old_slot = px[q_idx][1], int(sig_slot[OUT[i + 1]])
+                ok_kinds = px[q_idx][0] == K_RING and px[1 - q_idx][0] == K_ACC
+                if not ok_kinds:
+                    break
+                # canonical rows of a stage segment: all q rows, then all old rows (the olds are consecutive slots)
+                if extend:
+                    at = last_seg[3] + last_seg[1]
+                    tentative = cur.rows[:at] + [q_slot] + cur.rows[at:] + [old_slot]
+                else:
+                    tentative = cur.rows + [q_slot, old_slot]
+                if cur.fits_rows(2, tentative, not extend):
+                    break
+                close()
+            if ok_kinds:
+                if not extend:
+                    cur.segs.append([SEG_XM, 0, len(cur.recs), len(cur.rows), 0])
+                    cur.sealed = False
+                    n_seg_kind[SEG_XM] += 1
+                seg = cur.segs[-1]
+                cur.rows.insert(seg[3] + seg[1], q_slot)
+                cur.rows.append(old_slot)
+                pattern_row = {}
+                # records: XOR(acc, q); MUX(G, acc, old) -> out; their rows are the segment's by convention
+                block_of_op[i] = block_of_op[i + 1] = len(blocks)
+                if cur.first_op < 0:
+                    cur.first_op = i
+                cur.recs.append([0 | (OP_XOR << 24), 0 | ((K_ACC | (K_RING << 3)) << 24), 0, 0])
+                out_slot = old_slot
+                stash_out = stash_of[i + 1] + 1 if (i + 1) in stash_of else 0
+                cur.recs.append([0 | ((OP_MUX | F_STORE) << 24), 0 | ((K_GREG | (K_ACC << 3)) << 24),
+                                 0 | (K_RING << 24), out_slot | (stash_out << 24)])
+                cur.stored.add(out_slot)
+                n_acc += 2
+                n_greg += 1
+                n_ring += 2
+                n_elided += 1
+                seg[1] += 1
+                if (i + 1) in stash_of:
+                    seg[4] = stash_of[i + 1] + 1
+                    cur.sealed = True
+                n_units[SEG_XM] += 1
+                i += 2
+                continue
+            cls[i] = cls[i + 1] = ""                          # fall through: generic records
+            c = ""
+        # generic record
+        for attempt in (0, 1):
+            plan = operand_plan(i)
+            rows = new_generic_rows(plan)
+            last_seg = cur.segs[-1] if cur.segs else None
+            extend = last_seg is not None and last_seg[0] == SEG_GENERIC and last_seg[2] + last_seg[1] == len(cur.recs)
+            if cur.fits(1, rows, not extend):
+                break
+            close()
+        if not extend:
+            cur.segs.append([SEG_GENERIC, 0, len(cur.recs), 0, 0])
+            n_seg_kind[SEG_GENERIC] += 1
+        pattern_row = {}
+        add_record(i, plan, SEG_GENERIC, False)
+        cur.segs[-1][1] += 1
+        i += 1
+    close()
+    n_blocks = len(blocks)
 
-        def ka(w):
-            return (w[1] >> 24) & 7
-
-        def kb(w):
-            return (w[1] >> 27) & 7
-
-        def kc(w):
-            return (w[2] >> 24) & 7
-
-        def is_m(w):
-            return (w[0] >> 24) == (OP_MUX | F_STORE) and ka(w) == K_GREG and kc(w) == K_RING
-
-        def is_x(w):
-            return ((w[0] >> 24) == OP_XOR and ka(w) == K_ACC and kb(w) == K_RING and kc(w) == K_NONE and
-                    (w[3] >> 24) == 0)
-
-        pat = 0
-        rows_now = [int(x) for x in stream[b, 4:4 + (int(stream[b, 0]) & 0xFF)]]
-        R0 = 4 + RING_ROWS
-        if all(is_m(blk[q]) for q in range(n)) and all(kb(blk[q]) == K_ACC for q in range(1, n)) and kb(blk[0]) != K_NONE:
-            # canonical rows: row u = old value of unit u (its slot is also the slot unit u stores to), then the
-            # row the head takes its data from, if it takes it from the ring
-            new_rows = [rows_now[blk[q][2] & M24] for q in range(n)]
-            if all(new_rows[q] == (blk[q][3] & M24) for q in range(n)):
-                for q in range(n):
-                    stream[b, R0 + 4 * q + 2] = q | (K_RING << 24)
-                if kb(blk[0]) == K_RING:
-                    new_rows.append(rows_now[blk[0][1] & M24])
-                    stream[b, R0 + 1] = n | (int(stream[b, R0 + 1]) & 0xFF000000)
-                pat = PAT_MUX | (n << 4)                     # only the head of a chain may take its data from elsewhere
-        elif n % 2 == 0 and all(is_x(blk[q]) and is_m(blk[q + 1]) and kb(blk[q + 1]) == K_ACC
-                                for q in range(0, n, 2)):
-            # canonical rows: 2u = the row XORed in, 2u + 1 = old value of the stage's register (= its store slot)
-            new_rows = []
-            for q in range(0, n, 2):
-                new_rows += [rows_now[blk[q][1] & M24], rows_now[blk[q + 1][2] & M24]]
-            if all(new_rows[q + 1] == (blk[q + 1][3] & M24) for q in range(0, n, 2)):
-                for q in range(0, n, 2):
-                    stream[b, R0 + 4 * q + 1] = q | (int(stream[b, R0 + 4 * q + 1]) & 0xFF000000)
-                    stream[b, R0 + 4 * (q + 1) + 2] = (q + 1) | (K_RING << 24)
-                pat = PAT_XM | ((n // 2) << 4)
-        if pat:
-            stream[b, 0] = (int(stream[b, 0]) & ~0xFF) | len(new_rows) | (pat << 16)
-            stream[b, 4:4 + RING_ROWS] = 0
-            stream[b, 4:4 + len(new_rows)] = new_rows
-            if any(w[3] >> 24 for w in blk[:n]):
-                stream[b, 0] |= M_STASH
-            n_pat[pat & 15] += 1
+    # ---- encode ----------------------------------------------------------------------------------------------
+    stream = np.zeros((n_blocks, BLOCK_WORDS), dtype=np.uint32)
+    max_rows = max_runs = 0
+    for b, blk in enumerate(blocks):
+        runs = pieces(blk.rows)
+        assert len(blk.rows) <= RING_ROWS and len(runs) <= MAX_RUNS and len(blk.segs) <= MAX_SEG and len(blk.recs) <= BLOCK
+        flags = (M_FENCE if b % FENCE_PERIOD == 0 else 0)
+        if blk.guard >= 0:
+            flags |= M_GUARD
+            e = regions[blk.guard][1]
+            last_block = block_of_op[e - 1]
+            stream[b, 1] = last_block - b                    # blocks b+1 .. last_block are the region
+        stream[b, 0] = len(blk.rows) | flags | (len(blk.segs) << 16) | (len(runs) << 24)
+        stream[b, 2] = len(blk.recs)
+        for k, (kind, count, first_rec, first_row, stash_out) in enumerate(blk.segs):
+            head_acc = kind == SEG_MUX and ((blk.recs[first_rec][1] >> 27) & 7) == K_ACC
+            stream[b, W_SEG + k] = (kind | (count << 2) | (first_rec << 8) | (first_row << 13) | (stash_out << 18) |
+                                    (int(head_acc) << 24))
+        for k, (first_row, lg) in enumerate(runs):
+            stream[b, W_RUN + k] = blk.rows[first_row] | ((first_row | (lg << 5)) << 24)
+        stream[b, W_SLOT:W_SLOT + len(blk.rows)] = blk.rows
+        for u, rec in enumerate(blk.recs):
+            stream[b, W_REC + 4 * u: W_REC + 4 * u + 4] = rec
+        max_rows = max(max_rows, len(blk.rows))
+        max_runs = max(max_runs, len(runs))
 
     is_gate = np.asarray(ops.is_gate, dtype=bool)
     arity_tab = np.zeros(256, dtype=np.int64)
@@ -571,13 +673,17 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
         sig_slot=sig_slot, sig_shadow={}, sig_kept=kept, n_gates=int(is_gate.sum()), n_ops=n_ops,
         gate_words_bytes=gw_bytes, constants=constants, max_level_gates=n_ops, records_hinted=None, serial=True)
     guarded = sum(e - b for b, e, _ in regions)
-    prog.serial_info = {"blocks": n_blocks, "ops": n_ops, "acc_operands": n_acc, "stash_operands": n_stash,
-                        "ring_operands": n_ring, "late_operands": n_late, "guard_register_operands": n_greg,
-                        "stores_elided": n_elided, "stash_entries_used": len(set(stash_of.values())),
-                        "regions": len(regions), "guarded_ops": guarded, "padding": n_rec - n_ops - len(regions),
-                        "ring_rows_staged": int((stream[:, 0] & 0xFF).sum()) if n_blocks else 0,
-                        "max_ring_rows": int((stream[:, 0] & 0xFF).max()) if n_blocks else 0,
-                        "blocks_mux_chain": n_pat[PAT_MUX], "blocks_xor_mux": n_pat[PAT_XM]}
+    n_recs_total = sum(len(blk.recs) for blk in blocks)
+    prog.serial_info = {"blocks": n_blocks, "ops": n_ops, "records": n_recs_total, "acc_operands": n_acc,
+                        "stash_operands": n_stash, "ring_operands": n_ring, "late_operands": n_late,
+                        "guard_register_operands": n_greg, "stores_elided": n_elided,
+                        "stash_entries_used": len(set(stash_of.values())), "regions": len(regions), "guarded_ops": guarded,
+                        "ring_rows_staged": int(sum(len(blk.rows) for blk in blocks)),
+                        "tma_boxes": int(sum(len(pieces(blk.rows)) for blk in blocks)),
+                        "max_ring_rows": max_rows, "max_runs": max_runs,
+                        "segments": {"generic": n_seg_kind[SEG_GENERIC], "mux_chain": n_seg_kind[SEG_MUX],
+                                     "xor_mux": n_seg_kind[SEG_XM], "guard": n_seg_kind[SEG_GUARD]},
+                        "mux_chain_units": n_units[SEG_MUX], "xor_mux_units": n_units[SEG_XM]}
     return prog
 
 
@@ -591,17 +697,19 @@ def compile_circuit_serial(root, map_pins: bool = True, **kw) -> Program:
 def decode_block(line):
     """One control line -> dict (see the module docstring)."""
     w = [int(x) for x in np.asarray(line, dtype=np.uint32)]
+    n_rows, n_seg, n_runs, n_recs = w[0] & 0xFF, (w[0] >> 16) & 0xFF, w[0] >> 24, w[2]
     recs = []
-    for u in range(BLOCK):
-        w0, w1, w2, w3 = w[4 + RING_ROWS + 4 * u: 8 + RING_ROWS + 4 * u]
+    for u in range(n_recs):
+        w0, w1, w2, w3 = w[W_REC + 4 * u: W_REC + 4 * u + 4]
         flags = w0 >> 24
         recs.append({"op": flags & 15, "neg": bool(flags & F_NEG), "store": bool(flags & F_STORE),
                      "fields": (w0 & 0xFFFFFF, w1 & 0xFFFFFF, w2 & 0xFFFFFF), "out": w3 & 0xFFFFFF,
                      "stash_out": (w3 >> 24) - 1, "kinds": ((w1 >> 24) & 7, (w1 >> 27) & 7, (w2 >> 24) & 7)})
-    n_rows = w[0] & 0xFF
-    return {"n_rows": n_rows, "guard": bool(w[0] & M_GUARD), "fence": bool(w[0] & M_FENCE), "stash": bool(w[0] & M_STASH),
-            "pattern": (w[0] >> 16) & 15, "units": (w[0] >> 20) & 0xFF, "span": w[1], "n_recs": w[2],
-            "rows": w[4:4 + n_rows], "records": recs}
+    segs = [{"kind": x & 3, "count": (x >> 2) & 63, "first_rec": (x >> 8) & 31, "first_row": (x >> 13) & 31,
+             "stash_out": ((x >> 18) & 63) - 1} for x in w[W_SEG:W_SEG + n_seg]]
+    runs = [{"slot": x & 0xFFFFFF, "first_row": (x >> 24) & 31, "rows": 1 << (x >> 29)} for x in w[W_RUN:W_RUN + n_runs]]
+    return {"n_rows": n_rows, "guard": bool(w[0] & M_GUARD), "fence": bool(w[0] & M_FENCE), "span": w[1],
+            "rows": w[W_SLOT:W_SLOT + n_rows], "segments": segs, "runs": runs, "records": recs}
 
 
 def decode(stream: np.ndarray):

@@ -196,10 +196,20 @@ class CpuRuntime:
             queue = deque()                        # (block index, rows) staged and not yet consumed
             prod = {"b": 0, "step": 0, "blocked": False}
 
+            def stage(blk):
+                """What the producer's TMA boxes put into the ring group: box k covers 2^lg consecutive slots."""
+                ring = [None] * blk["n_rows"]
+                for run in blk["runs"]:
+                    for k in range(run["rows"]):
+                        ring[run["first_row"] + k] = fetch_row(run["slot"] + k)
+                assert all(r is not None for r in ring), "ring rows not covered by the block's TMA runs"
+                assert [run["slot"] + k for run in blk["runs"] for k in range(run["rows"])] == list(blk["rows"])
+                return ring
+
             def pump():
                 while not prod["blocked"] and prod["step"] < steps and len(queue) < (S.GB_MAX if early else 1):
                     blk = blocks[prod["b"]]
-                    queue.append((prod["b"], [fetch_row(s) for s in blk["rows"]]))
+                    queue.append((prod["b"], stage(blk)))
                     if blk["guard"]:
                         prod["blocked"] = True
                     else:
@@ -231,34 +241,37 @@ class CpuRuntime:
                         return np.zeros(n, dtype=U64)
 
                     recs = blk["records"]
-                    if blk["pattern"] == S.PAT_MUX:          # the kernel's conventions: ring row u, store slot = fetch word u
-                        d = operand(recs[0]["kinds"][1], recs[0]["fields"][1])
-                        for u in range(blk["units"]):
-                            d = (greg & d) | (~greg & ring[u])
-                            store(blk["rows"][u], d)
-                            if blk["stash"] and recs[u]["stash_out"] >= 0:
-                                stash[recs[u]["stash_out"]] = d
-                        acc = d
-                    elif blk["pattern"] == S.PAT_XM:
-                        for u in range(blk["units"]):
-                            acc = (greg & (acc ^ ring[2 * u])) | (~greg & ring[2 * u + 1])
-                            store(blk["rows"][2 * u + 1], acc)
-                            if blk["stash"] and recs[2 * u + 1]["stash_out"] >= 0:
-                                stash[recs[2 * u + 1]["stash_out"]] = acc
-                    else:
-                        for r in recs[:blk["n_recs"]]:
-                            if r["op"] in (0, 11):
-                                continue
-                            vals = [operand(k, f) for k, f in zip(r["kinds"], r["fields"])]
-                            res = _apply(int(r["op"] | (0x80 if r["neg"] else 0)), vals[0], vals[1], vals[2])
-                            if r["store"]:
-                                store(r["out"], res)
-                            if r["stash_out"] >= 0:
-                                stash[r["stash_out"]] = res
-                            acc = res
+                    guard_rec = None
+                    for seg in blk["segments"]:
+                        f, n, r0 = seg["first_rec"], seg["count"], seg["first_row"]
+                        if seg["kind"] == S.SEG_MUX:          # the kernel's conventions: ring row r0 + u, store slot = its slot
+                            d = operand(recs[f]["kinds"][1], recs[f]["fields"][1])
+                            for u in range(n):
+                                d = (greg & d) | (~greg & ring[r0 + u])
+                                store(blk["rows"][r0 + u], d)
+                            acc = d
+                            if seg["stash_out"] >= 0:         # only the segment's last value can go to the stash
+                                stash[seg["stash_out"]] = acc
+                        elif seg["kind"] == S.SEG_XM:
+                            for u in range(n):
+                                acc = (greg & (acc ^ ring[r0 + u])) | (~greg & ring[r0 + n + u])
+                                store(blk["rows"][r0 + n + u], acc)
+                            if seg["stash_out"] >= 0:
+                                stash[seg["stash_out"]] = acc
+                        elif seg["kind"] == S.SEG_GUARD:
+                            guard_rec = recs[f]
+                        else:
+                            for r in recs[f:f + n]:
+                                vals = [operand(k, fl) for k, fl in zip(r["kinds"], r["fields"])]
+                                res = _apply(int(r["op"] | (0x80 if r["neg"] else 0)), vals[0], vals[1], vals[2])
+                                if r["store"]:
+                                    store(r["out"], res)
+                                if r["stash_out"] >= 0:
+                                    stash[r["stash_out"]] = res
+                                acc = res
                     skip = 0
                     if blk["guard"]:
-                        g = recs[7]
+                        g = guard_rec
                         greg = operand(g["kinds"][0], g["fields"][0]).copy()
                         unpublished.clear()                    # consumers fence before they vote
                         if not greg.any():

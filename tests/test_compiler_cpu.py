@@ -427,3 +427,45 @@ def test_sort_level_by_fanin_keeps_levels_and_results():
         e.randomize_inputs()
         e.step()
     assert all(np.array_equal(ea.get_pin_planes(p), eb.get_pin_planes(p)) for p in ea.output_pins())
+
+
+# ---- the Adder primitive lowered as a word-level parallel-prefix network ---------------------------
+@pytest.mark.parametrize("case", golden("adder.json"), ids=lambda c: c["name"])
+@pytest.mark.parametrize("mode", ["levels", "serial"])
+def test_adder_prefix_lowering_matches_reference_jit_vectors(case, mode):
+    """Same function as the ripple lowering (and as the reference JIT: simulator.py:135-147), logarithmic depth."""
+    w = case["width"]
+    top = MD.Composite()
+    top.add_child("add", MD.Adder(w))
+    vecs = case["vectors"]
+    lanes = (len(vecs) + 63) // 64 * 64
+    pad = lanes - len(vecs)
+    eng = B200Engine(top, 1, True, lanes=lanes, runtime=CpuRuntime(), mode=mode, adder_prefix=True)
+    col = lambda k: np.array([v[k] for v in vecs] + [0] * pad, dtype=np.uint64)
+    eng.set_pin_state("/add/a", col(0))
+    eng.set_pin_state("/add/b", col(1))
+    eng.set_pin_state("/add/cin", col(2))
+    eng.step()
+    s = eng.get_pin_state("/add/sum", lanes=True)
+    c = eng.get_pin_state("/add/cout", lanes=True)
+    for i, (ws, wc) in enumerate(case["results"]):
+        assert (int(s[i]), int(c[i])) == (ws, wc), (w, vecs[i])
+    if mode == "levels" and w >= 16:
+        ripple = compiler.compile_circuit(top)
+        assert eng.program.n_levels <= 2 * int(np.ceil(np.log2(w))) + 8 < ripple.n_levels
+
+
+def test_adder_prefix_lowering_in_random_circuits_with_feedback():
+    """Adders whose outputs feed their own inputs (aliasing) and sit in feedback loops: prefix == ripple == oracle."""
+    from oracle import restate
+    for seed in range(500, 512):
+        prims = ("Gate", "Not", "Constant", "Clock", "Counter", "Adder", "Adder", "Adder", "Register")
+        root, probes = circuits.random_circuit(MD, seed, n_nodes=22, primitives=prims)
+        ora = restate.RestatedJIT(root, 3, True, lanes=64)
+        engs = [B200Engine(root, 3, True, lanes=64, runtime=CpuRuntime(), mode=m, adder_prefix=True) for m in ("levels", "serial")]
+        for step in range(8):
+            ora.step()
+            for e in engs:
+                e.step()
+                for p in probes:
+                    assert e.get_pin_state(p) == ora.get_pin_state(p), (seed, step, p, e.mode)

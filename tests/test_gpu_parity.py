@@ -419,3 +419,60 @@ def test_gpu_c_abi_entry_points_directly(cuda_rt):
     bad = rt.make_state(plane, stride - 1, None, 0, n_slots, n_slots, words)    # odd stride
     with pytest.raises(RuntimeError, match="strides must be even"):
         rt.eval_levels(d_recs, off, 0, 2, bad)
+
+
+# ---- K1t: the level kernel with rows staged through shared memory by TMA bulk copies --------------------------
+@pytest.fixture
+def level_tma(cuda_rt):
+    old = cuda_rt.set_tuning("level_tma", 1)
+    yield
+    cuda_rt.set_tuning("level_tma", old)
+
+
+@pytest.mark.parametrize("case", [c for c in golden("traces.json") if not c["name"].startswith("fuzz_seed3")][:24],
+                         ids=lambda c: c["name"])
+def test_gpu_level_tma_traces(level_tma, case):
+    run_trace_case(case, lambda root, bs: B200Engine(root, bs, True, mode="levels"))
+
+
+@pytest.mark.parametrize("case", golden("lane_trick.json"), ids=lambda c: c["name"])
+@pytest.mark.parametrize("tile_words", [None, 16, 48])
+def test_gpu_level_tma_lane_trick(level_tma, case, tile_words):
+    """Reference-JIT words on ragged lane counts and tile sizes (rows of 8 x odd words, several tiles, 2 streams)."""
+    ins, outs = lane_trick_planes(case)
+    nw = case["n_words"]
+    reps = 11
+    eng = B200Engine(build(case), 1, True, lanes=64 * nw * reps, mode="levels", keep="ports", tile_words=tile_words)
+    for p, words in ins.items():
+        eng.set_pin_planes(p, np.tile(words, reps)[None, :])
+    eng.step()
+    for p, words in outs.items():
+        assert np.array_equal(eng.get_pin_planes(p)[0], np.tile(words, reps)), p
+
+
+@pytest.mark.parametrize("seed", range(240, 260))
+def test_gpu_level_tma_vs_oracle_all_lanes(level_tma, seed):
+    root, probes = circuits.random_circuit(MD, seed, n_nodes=22)
+    d = compiler.flatten(root)
+    lane_inputs = [(p, d.pin_width[d.find_pin(p)]) for p in ("/in0/pin", "/in1/pin")]
+    lanes = (64, 192, 1024, 4160, 64 * 513)[seed % 5]
+    compare_engine_to_oracle(lambda M: circuits.random_circuit(M, seed, n_nodes=22),
+                             lambda r, bs, n: gpu_factory("levels")(r, bs, n),
+                             lanes=lanes, steps=6, probes=probes, lane_inputs=lane_inputs, seed=seed)
+
+
+def test_gpu_level_tma_c5_20k_vs_oracle(level_tma):
+    from oracle import cref, restate
+    root = circuits.random_dag(MD, n_gates=20_000, depth=40, n_inputs=256, seed=77)
+    lanes = 64 * 1100                                    # 512-word tiles, the last one ragged (76 words)
+    eng = B200Engine(root, 1, True, lanes=lanes, keep="ports", mode="levels", tile_words=512)
+    assert eng.n_tiles == 3
+    eng.randomize_inputs()
+    eng.step()
+    eng.step()
+    ora = cref.CRef(root, 1, True, lanes=lanes)
+    ora.set_rows(ora._base("/i0/pin"), restate.stimulus_word(np.arange(256)[:, None], np.arange(eng.words)[None, :]))
+    ora.step()
+    want = ora.rows(ora._base("/o0/pin"), 500)
+    got = np.stack([eng.get_pin_planes(p)[0] for p in eng.output_pins()])
+    assert np.array_equal(got, want)

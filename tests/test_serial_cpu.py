@@ -157,32 +157,71 @@ def check_stream_invariants(prog):
     blocks = list(serial.decode(prog.records))
     nb = len(blocks)
     n_slots = prog.n_persist + prog.n_scratch
-    stores = [[r["out"] for r in blk["records"] if r["store"] and r["op"] not in (0, serial.OP_GUARD)] for blk in blocks]
+    stores = []
+    for blk in blocks:
+        st = set()
+        for seg in blk["segments"]:
+            f, n, r0 = seg["first_rec"], seg["count"], seg["first_row"]
+            if seg["kind"] == serial.SEG_MUX:
+                st.update(blk["rows"][r0:r0 + n])
+            elif seg["kind"] == serial.SEG_XM:
+                st.update(blk["rows"][r0 + n:r0 + 2 * n])
+            elif seg["kind"] == serial.SEG_GENERIC:
+                st.update(r["out"] for r in blk["records"][f:f + n] if r["store"])
+        stores.append(st)
     for b, blk in enumerate(blocks):
-        assert blk["n_rows"] <= serial.RING_ROWS and (blk["pattern"] or len(set(blk["rows"])) == blk["n_rows"])
-        if blk["pattern"] == serial.PAT_MUX:
-            assert all(blk["rows"][u] == blk["records"][u]["out"] for u in range(blk["units"]))
-        if blk["pattern"] == serial.PAT_XM:
-            assert all(blk["rows"][2 * u + 1] == blk["records"][2 * u + 1]["out"] for u in range(blk["units"]))
+        assert blk["n_rows"] <= serial.RING_ROWS and len(blk["runs"]) <= serial.MAX_RUNS
+        assert len(blk["segments"]) <= serial.MAX_SEG and len(blk["records"]) <= serial.BLOCK
         assert blk["fence"] == (b % serial.FENCE_PERIOD == 0)
+        covered = [run["slot"] + k for run in blk["runs"] for k in range(run["rows"])]
+        assert covered == list(blk["rows"]) and all(s < n_slots for s in covered)
+        for run in blk["runs"]:                          # a TMA box lies in one plane
+            assert (run["slot"] < prog.n_persist) == (run["slot"] + run["rows"] - 1 < prog.n_persist)
         stored = set()
-        for u, r in enumerate(blk["records"]):
-            if r["op"] == serial.OP_GUARD:
-                assert u == serial.BLOCK - 1 and blk["guard"] and b + 1 + blk["span"] <= nb
-            elif u == serial.BLOCK - 1:
-                assert not blk["guard"]
-            if r["op"] == 0:
+        seen_recs = 0
+        for k, seg in enumerate(blk["segments"]):
+            f, n, r0 = seg["first_rec"], seg["count"], seg["first_row"]
+            assert f == seen_recs
+            if seg["kind"] == serial.SEG_GUARD:
+                assert k == len(blk["segments"]) - 1 and blk["guard"] and b + 1 + blk["span"] <= nb
+                r = blk["records"][f]
+                if r["kinds"][0] == serial.K_RING:
+                    assert blk["rows"][r["fields"][0]] not in stored
+                seen_recs += 1
                 continue
-            for kind, f in zip(r["kinds"], r["fields"]):
-                if kind == serial.K_RING:
-                    assert f < blk["n_rows"] and blk["rows"][f] not in stored, "ring row stored earlier in its block"
-                if kind == serial.K_LATE:
-                    assert f < n_slots
-                if kind == serial.K_STASH:
-                    assert f < serial.STASH_N
-            if r["store"] and r["op"] != serial.OP_GUARD:
-                assert r["out"] < n_slots
-                stored.add(r["out"])
+            if seg["kind"] == serial.SEG_MUX:
+                r = blk["records"][f]
+                if r["kinds"][1] == serial.K_RING:
+                    assert blk["rows"][r["fields"][1]] not in stored
+                for u in range(n):
+                    rec = blk["records"][f + u]
+                    assert rec["op"] == 6 and rec["store"] and rec["out"] == blk["rows"][r0 + u]
+                    assert rec["stash_out"] == (seg["stash_out"] if u == n - 1 else -1)
+                    assert blk["rows"][r0 + u] not in stored, "ring row stored earlier in its block"
+                    stored.add(rec["out"])
+                seen_recs += n
+            elif seg["kind"] == serial.SEG_XM:
+                for u in range(n):
+                    assert blk["rows"][r0 + u] not in stored and blk["rows"][r0 + n + u] not in stored
+                    assert blk["records"][f + 2 * u + 1]["out"] == blk["rows"][r0 + n + u]
+                    assert blk["records"][f + 2 * u + 1]["stash_out"] == (seg["stash_out"] if u == n - 1 else -1)
+                    stored.add(blk["rows"][r0 + n + u])
+                seen_recs += 2 * n
+            else:
+                for rec in blk["records"][f:f + n]:
+                    for kind, fl in zip(rec["kinds"], rec["fields"]):
+                        if kind == serial.K_RING:
+                            assert fl < blk["n_rows"] and blk["rows"][fl] not in stored, "ring row stored earlier in its block"
+                        if kind == serial.K_LATE:
+                            assert fl < n_slots
+                        if kind == serial.K_STASH:
+                            assert fl < serial.STASH_N
+                    if rec["store"]:
+                        assert rec["out"] < n_slots
+                        stored.add(rec["out"])
+                seen_recs += n
+        assert seen_recs == len(blk["records"])
+        assert not blk["guard"] or blk["segments"][-1]["kind"] == serial.SEG_GUARD
         # no store to a staged row between the point that publishes stores to the producer and this block
         k = b - 1
         scanned = 0
