@@ -96,18 +96,21 @@ int mcb_latch(const uint32_t *d_latch_records, int n, const mcb_state *st, void 
 int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
             const mcb_state *st, int64_t steps, int mode, void *stream);
 
-/* K3 v3 - streamed serial run.  Replaces `step()` / `burst()` (core/simulator.py:195-245, :293-297)
+/* K3 - streamed serial run.  Replaces `step()` / `burst()` (core/simulator.py:195-245, :293-297)
  * in the reference's own execution model: every micro-op in emit order, in place, `steps` times,
  * each consumer thread on its own (slice of a) lane column, ONE launch for any number of steps.
- * `d_stream` (16-byte aligned) holds `n_blocks` control lines of 52 words (mcircuit_b200/serial.py):
- * 4 meta words, 16 slots of the rows to stage, 8 records of four `field(24) | meta(8) << 24` words.
- * A producer warp per CTA stages each block's control line and rows into a shared-memory ring
- * with cp.async.bulk + mbarriers ahead of four consumer warps; operands come from the ring, from
- * per-thread stash words in shared memory, from the accumulator (the previous record's result),
- * from the guard register, or - for rows stored too recently to be staged - from an ordinary
- * load; a GUARD record lets a CTA whose enable word is zero in every lane jump over its region.
+ * `d_stream` (16-byte aligned) holds `n_blocks` control lines of 192 words (mcircuit_b200/serial.py):
+ * 4 meta words, 12 segment words, 16 TMA runs, 32 row slots, 32 records of four
+ * `field(24) | meta(8) << 24` words.  A producer warp per CTA stages each block's control line
+ * (cp.async.bulk) and its state rows (one cp.async.bulk.tensor.2d per run of 2^k consecutive slots;
+ * the tensor maps of the state planes are encoded and cached inside the library) into a
+ * shared-memory ring, handed to four consumer warps through mbarriers; operands come from the ring,
+ * from per-thread stash words in shared memory, from the accumulator (the previous record's
+ * result), from the guard register, or - for rows stored too recently to be staged - from an
+ * ordinary load; a GUARD segment lets a CTA whose enable word is zero in every lane jump over its
+ * region.  State rows and `d_stream` must be 16-byte aligned, row strides multiples of 16 bytes.
  * `word_bytes`: low byte = bytes of a lane word one thread owns (0 = 8; 8, 4, 2 or 1); bits 8.. =
- * rows a ring group must hold (0 = 16, the format's maximum).
+ * rows a ring group must hold (0 = 32, the format's maximum).
  * `d_skipped`: optional device counter, += the guarded regions CTA 0 jumped over.             */
 int mcb_run_serial(const uint32_t *d_stream, int n_blocks, const mcb_state *st, int64_t steps,
                    int word_bytes, uint64_t *d_skipped, void *stream);
@@ -180,7 +183,11 @@ int mcb_graph_cache_clear(void);
 int mcb_graph_cache_clear_owner(const uint32_t *d_records);
 int mcb_graph_cache_size(void);
 
-/* tuning knobs (block size, gates per block ...); returns the previous value              */
+/* tuning knobs; returns the previous value.  Keys: level_block, level_unroll, level_ctas_per_sm,
+ * level_cache, level_pdl (programmatic dependent launch between levels), level_tma (1 = K1t: rows
+ * staged in shared memory by cp.async.bulk, tiles of <= 512 lane words), resident_*, persist_*,
+ * serial_word_bytes, stream_groups (ring groups of K3, 0 = as many as fit, <= 8),
+ * stream_smem_kb (shared memory K3 may take per CTA, 0 = the device maximum)                */
 int mcb_set_tuning(const char *key, int value);
 /* every knob back to the shipped default                                                   */
 int mcb_reset_tuning(void);

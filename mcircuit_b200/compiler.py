@@ -413,6 +413,7 @@ class _Ops:
         self.allow3 = allow3
         self.dead = set()                 # pin signals orphaned by edge-detector sharing
         self.net_sig = None               # this compile's net -> first signal map (a COPY of the design's)
+        self.shared_prev = set()          # prevclock signals that stand for a whole group of Registers / Counters
 
     def temp(self) -> int:
         t = self.n_sig
@@ -653,6 +654,7 @@ def lower(design: Design, allow3: bool = True, share_edge_detectors: bool = Fals
         hit = groups.get(key) if alone else None
         if hit is not None:
             rise, leader_prev = hit
+            ops.shared_prev.add(int(leader_prev))
             ops.dead.add(p["prevclock"][0])
             net_sig[pin_net[prev_pin]] = leader_prev            # the pin now views the leader's bit
             lower_fn(ops, design.leaf_desc[leaf], p["clock"], *mid, range(leader_prev, leader_prev + 1),
@@ -730,6 +732,7 @@ class Program:
     records_hinted: Optional[np.ndarray] = None   # records + streaming hints (bit 31 of in0/in1)
     net_sig: Optional[np.ndarray] = None          # net -> first signal of THIS compile (edge-detector sharing redirects some)
     serial: bool = False                          # records are a serial stream (compile_serial), not levels
+    shared_prev: Optional[set] = None             # prevclock signals shared by a group of clocked primitives
 
     @property
     def n_slots(self) -> int:
@@ -1034,7 +1037,7 @@ def compile_design(design: Design, keep="all", observe: Sequence[str] = (),
             constants.append((base, design.pin_width[pin], int(desc.value)))
 
     return Program(
-        net_sig=ops.net_sig,
+        net_sig=ops.net_sig, shared_prev=set(ops.shared_prev),
         design=design, records=records, level_off=level_off.astype(np.int32),
         n_levels=n_levels, has_latch=has_latch, n_persist=n_persist, n_scratch=n_scratch,
         sig_slot=sig_slot, sig_shadow={s: int(sig_slot[sh]) for s, sh in shadow_sig.items()},

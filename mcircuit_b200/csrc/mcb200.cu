@@ -1480,12 +1480,22 @@ __device__ __forceinline__ uint64_t block_sum(uint64_t x, uint64_t *sh) {
 
 __global__ void __launch_bounds__(256)
 k_signature(const int *__restrict__ slots, int n, View v, long long col_offset,
-            uint64_t *popcount, uint64_t *checksum) {
+            uint64_t *popcount, uint64_t *checksum, long long chunk_words) {
+    // grid.y splits a row into column chunks when there are fewer rows than the GPU needs CTAs; the
+    // partial sums of a row then meet in its (zeroed) result words by atomicAdd - sums mod 2^64 commute
     __shared__ uint64_t sh[8];
+    const long long j0 = (long long)blockIdx.y * chunk_words;
+    const long long j1 = j0 + chunk_words < v.n_words ? j0 + chunk_words : v.n_words;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint64_t *r = row(v, (uint32_t)slots[i]);
         uint64_t pc = 0, cs = 0;
-        for (long long j = threadIdx.x; j < v.n_words; j += blockDim.x) {
+        long long j = j0 + 2ll * threadIdx.x;
+        for (; j + 1 < j1; j += 2ll * blockDim.x) {              // rows are 16-byte aligned, chunks even
+            const ulonglong2 w = *reinterpret_cast<const ulonglong2 *>(r + j);
+            pc += (uint64_t)__popcll(w.x) + (uint64_t)__popcll(w.y);
+            cs += w.x * (2ull * (uint64_t)(col_offset + j) + 1ull) + w.y * (2ull * (uint64_t)(col_offset + j + 1) + 1ull);
+        }
+        if (j < j1) {
             const uint64_t w = r[j];
             pc += (uint64_t)__popcll(w);
             cs += w * (2ull * (uint64_t)(col_offset + j) + 1ull);
@@ -1493,27 +1503,34 @@ k_signature(const int *__restrict__ slots, int n, View v, long long col_offset,
         pc = block_sum(pc, sh);
         cs = block_sum(cs, sh);
         if (threadIdx.x == 0) {
-            if (popcount) popcount[i] = pc;
-            if (checksum) checksum[i] = cs;
+            if (gridDim.y == 1) {
+                if (popcount) popcount[i] = pc;
+                if (checksum) checksum[i] = cs;
+            } else {
+                if (popcount) atomicAdd(reinterpret_cast<unsigned long long *>(popcount + i), (unsigned long long)pc);
+                if (checksum) atomicAdd(reinterpret_cast<unsigned long long *>(checksum + i), (unsigned long long)cs);
+            }
         }
     }
 }
 
 __global__ void __launch_bounds__(256)
 k_toggle(const int *__restrict__ slots, int n, View v, uint64_t *shadow, long long shstride,
-         uint64_t *toggles) {
+         uint64_t *toggles, long long chunk_words) {
     __shared__ uint64_t sh[8];
+    const long long j0 = (long long)blockIdx.y * chunk_words;
+    const long long j1 = j0 + chunk_words < v.n_words ? j0 + chunk_words : v.n_words;
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const uint64_t *r = row(v, (uint32_t)slots[i]);
         uint64_t *sd = shadow + (long long)i * shstride;
         uint64_t t = 0;
-        for (long long j = threadIdx.x; j < v.n_words; j += blockDim.x) {
+        for (long long j = j0 + threadIdx.x; j < j1; j += blockDim.x) {
             const uint64_t w = r[j];
             t += (uint64_t)__popcll(w ^ sd[j]);
             sd[j] = w;
         }
         t = block_sum(t, sh);
-        if (threadIdx.x == 0) toggles[i] += t;
+        if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long *>(toggles + i), (unsigned long long)t);
     }
 }
 
@@ -1908,15 +1925,40 @@ int mcb_copy2d(void *dst, int64_t dst_pitch, const void *src, int64_t src_pitch,
     return 0;
 }
 
+// K4 grids: one CTA per row when there are enough rows, else rows are cut into even column chunks (>= 2,048 words)
+static void row_reduce_grid(int n, long long n_words, dim3 *grid, long long *chunk_words) {
+    const int want = sm_count() * 8;
+    int gx = n < want ? n : want;
+    long long chunks = 1;
+    if (n < want) {
+        chunks = want / (n > 0 ? n : 1);
+        const long long max_chunks = (n_words + 2047) / 2048;
+        if (chunks > max_chunks) chunks = max_chunks;
+        if (chunks < 1) chunks = 1;
+        if (chunks > 65535) chunks = 65535;
+    }
+    long long cw = (n_words + chunks - 1) / chunks;
+    cw = (cw + 1) / 2 * 2;
+    chunks = (n_words + cw - 1) / cw;
+    *grid = dim3((unsigned)gx, (unsigned)chunks, 1);
+    *chunk_words = cw;
+}
+
 int mcb_signature(const int32_t *d_slots, int n, const mcb_state *st, int64_t col_offset,
                   uint64_t *d_popcount, uint64_t *d_checksum, void *stream) {
     int rc = check_state(st);
     if (rc) return rc;
     if (n < 0 || (n > 0 && !d_slots)) return fail(MCB_ERR_ARG, "bad slot list");
     if (n == 0 || st->n_words == 0) return 0;
-    int grid = n < sm_count() * 8 ? n : sm_count() * 8;
+    dim3 grid;
+    long long chunk_words;
+    row_reduce_grid(n, st->n_words, &grid, &chunk_words);
+    if (grid.y > 1) {                                    // partial sums meet by atomicAdd
+        if (d_popcount) CUDA_TRY(cudaMemsetAsync(d_popcount, 0, (size_t)n * 8, (cudaStream_t)stream));
+        if (d_checksum) CUDA_TRY(cudaMemsetAsync(d_checksum, 0, (size_t)n * 8, (cudaStream_t)stream));
+    }
     k_signature<<<grid, 256, 0, (cudaStream_t)stream>>>(d_slots, n, make_view(st), col_offset,
-                                                         d_popcount, d_checksum);
+                                                         d_popcount, d_checksum, chunk_words);
     LAUNCH_CHECK("k_signature");
     return 0;
 }
@@ -1928,9 +1970,11 @@ int mcb_toggle_accum(const int32_t *d_slots, int n, const mcb_state *st, uint64_
     if (n < 0 || (n > 0 && (!d_slots || !d_shadow || !d_toggles)) || shadow_stride < st->n_words)
         return fail(MCB_ERR_ARG, "bad toggle arguments");
     if (n == 0 || st->n_words == 0) return 0;
-    int grid = n < sm_count() * 8 ? n : sm_count() * 8;
+    dim3 grid;
+    long long chunk_words;
+    row_reduce_grid(n, st->n_words, &grid, &chunk_words);
     k_toggle<<<grid, 256, 0, (cudaStream_t)stream>>>(d_slots, n, make_view(st), d_shadow,
-                                                      shadow_stride, d_toggles);
+                                                      shadow_stride, d_toggles, chunk_words);
     LAUNCH_CHECK("k_toggle");
     return 0;
 }

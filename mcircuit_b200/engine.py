@@ -57,10 +57,21 @@ class B200Engine(Executor):
                  mode="auto", runtime=None, lane_word_offset=0, program: Optional[Program] = None,
                  memory_budget: Optional[int] = None, back_edges="auto", resident_batch=0,
                  resident_word_bytes=0, in_flight=2, streams=None, level_hints=False,
-                 share_edge_detectors=False, sort_level_by_fanin=False, serial_guard=True,
+                 share_edge_detectors=None, sort_level_by_fanin=False, serial_guard=True,
                  serial_word_bytes=0, serial_options: Optional[dict] = None, adder_prefix=False):
         if lanes < 1 or lanes % 64:
             raise ValueError("lanes must be a positive multiple of 64 (one 64-bit word = 64 lanes)")
+        # Registers / Counters on one clock share one edge detector by default (29,089 -> 10,707 micro-ops on C4, and
+        # what lets K3 skip idle clock phases); a poke of ONE member's prevclock un-shares the engine on the fly
+        # (_unshare_edge_detectors), so the reference's per-primitive prevclock semantics are kept
+        if share_edge_detectors is None:
+            share_edge_detectors = program is None
+        self._ctor_kwargs = dict(lanes=lanes, device=device, keep=keep, observe=observe, tile_words=tile_words, mode=mode,
+                                 lane_word_offset=lane_word_offset, memory_budget=memory_budget, back_edges=back_edges,
+                                 resident_batch=resident_batch, resident_word_bytes=resident_word_bytes, in_flight=in_flight,
+                                 streams=streams, level_hints=level_hints, share_edge_detectors=share_edge_detectors,
+                                 sort_level_by_fanin=sort_level_by_fanin, serial_guard=serial_guard,
+                                 serial_word_bytes=serial_word_bytes, serial_options=serial_options, adder_prefix=adder_prefix)
         if runtime is None:
             from .runtime import CudaRuntime
             runtime = CudaRuntime(device)           # raises when there is no B200 / no .so
@@ -88,6 +99,17 @@ class B200Engine(Executor):
                 program = compiler.compile_design(design, keep=keep, observe=observe, back_edges=back_edges,
                                                   share_edge_detectors=share_edge_detectors,
                                                   sort_level_by_fanin=sort_level_by_fanin, adder_prefix=adder_prefix)
+                if mode == "auto" and (program.n_ops / max(1, program.n_levels)) * min(self.words, DEFAULT_TILE_WORDS) < (1 << 19):
+                    # narrow levels (sequential logic, long dependent chains): per-level launches would be launch
+                    # bound; run the reference's own emit order as one stream instead (K3: one launch for any
+                    # number of steps, rows staged by TMA, idle clock phases skipped)
+                    from . import serial
+                    try:
+                        program = serial.compile_serial(design, keep=keep, observe=observe,
+                                                        share_edge_detectors=share_edge_detectors, guard=serial_guard,
+                                                        adder_prefix=adder_prefix, **(serial_options or {}))
+                    except compiler.CircuitError:
+                        pass                                     # more than 2^24 slots: stay with the level program
         if getattr(program, "serial", False):
             if mode not in ("auto", "serial"):
                 raise ValueError("a serial program runs in mode='serial' only")
@@ -420,9 +442,18 @@ class B200Engine(Executor):
             self.rt.fill_rows(self.rt.to_device(np.asarray(slots, dtype=np.int32)),
                               self.rt.to_device(np.asarray(vals, dtype=np.uint64)), len(slots), self._whole)
 
+    def _before_poke(self, pin):
+        """A poke of one member's ``prevclock`` cannot be expressed while a group shares that bit."""
+        shared = getattr(self.program, "shared_prev", None)
+        if shared and self.program.design is not None:
+            base, _ = self.program.pin_signals(pin)            # KeyError on an unknown pin, as always
+            if base in shared:
+                self._unshare_edge_detectors()
+
     def set_pin_state(self, pin, value):
         """Scalar: every lane gets ``value`` (masked to the pin width).  Array of ``lanes``
         uint64: one value per lane."""
+        self._before_poke(pin)
         base, width, slots, shadows = self._slots_of(pin, need_value=False)
         if np.isscalar(value) or isinstance(value, int):
             self._poke_signals(base, width, int(value) & ((1 << width) - 1))
@@ -458,6 +489,7 @@ class B200Engine(Executor):
     # bit-plane access: rows of the slot-major state, no transposition
     def set_pin_planes(self, pin, planes):
         """planes: uint64[width, words] - bit b of every lane word, already bit-sliced."""
+        self._before_poke(pin)
         base, width, slots, shadows = self._slots_of(pin, need_value=False)
         p = np.ascontiguousarray(np.asarray(planes, dtype=np.uint64)).reshape(width, self.words)
         d = self.rt.to_device(p)
@@ -664,26 +696,41 @@ class B200Engine(Executor):
         return int(np.bitwise_xor.reduce(self.program.records.view(np.uint32).ravel().astype(np.uint64))) \
             if self.program.n_ops else 0
 
+    def _canonical_slots(self):
+        """int64[n_pin_signals]: for every bit of every net, in the DESIGN's own numbering (the same for every compile
+        of one circuit), the persistent slot that holds it in THIS program, or -1.  With shared edge detectors the
+        members' ``prevclock`` nets resolve to their leader's slot; a state net kept only through its 'prev'
+        shadow (levels mode) resolves to the shadow."""
+        prog = self.program
+        d = prog.design
+        P = prog.n_persist
+        widths = np.asarray(d.net_width, dtype=np.int64)
+        n_pin = int(widths.sum())
+        nets = np.repeat(np.arange(len(widths), dtype=np.int64), widths)
+        bits = np.arange(n_pin, dtype=np.int64) - np.asarray(d.net_sig, dtype=np.int64)[nets]
+        net_sig = np.asarray(prog.net_sig if prog.net_sig is not None else d.net_sig, dtype=np.int64)
+        sig = net_sig[nets] + bits
+        slots = np.asarray(prog.sig_slot, dtype=np.int64)[sig]
+        for s_, shadow in prog.sig_shadow.items():
+            if 0 <= shadow < P:
+                hit = (sig == s_) & ~((slots >= 0) & (slots < P))
+                slots[hit] = shadow
+        slots[(slots < 0) | (slots >= P)] = -1
+        return slots, sig
+
     def state_dict(self):
-        """Everything that survives a step: the persistent rows (all lanes), keyed by SIGNAL, and the
-        step count.  Scratch rows are dead between steps, so they are not saved.  Keyed by signal, a
-        checkpoint written by one execution mode (levels / resident / serial lay their slots out
-        differently) resumes in another engine of the same circuit."""
+        """Everything that survives a step: the persistent rows (all lanes), keyed by net bit, and the step count.
+        Scratch rows are dead between steps, so they are not saved.  Keyed by net, a checkpoint written under one
+        slot layout (levels / resident / serial, with or without shared edge detectors) resumes under another
+        engine of the same circuit."""
         prog = self.program
         P = prog.n_persist
         rows = self.rt.to_host_u64(self._plane[:P * self.stride]).reshape(P, self.stride)[:, :self.words]
-        n_pin = len(prog.sig_kept)
-        slots = np.asarray(prog.sig_slot[:n_pin], dtype=np.int64)
-        slots = slots.copy()
-        for sig, shadow in prog.sig_shadow.items():              # a state net kept only through its 'prev' shadow
-            if sig < n_pin and not (0 <= slots[sig] < P) and 0 <= shadow < P:
-                slots[sig] = shadow
-        sigs = np.nonzero((slots >= 0) & (slots < P))[0]
-        shared = prog.net_sig is not None and not np.array_equal(prog.net_sig, prog.design.net_sig) \
-            if prog.design is not None else False
-        return {"persist": np.ascontiguousarray(rows), "steps_done": self.steps_done, "lanes": self.lanes,
-                "n_persist": P, "records_crc": self._records_crc(), "signals": sigs.astype(np.int64),
-                "signal_slots": slots[sigs], "n_pin_signals": n_pin, "shared_edge_detectors": bool(shared)}
+        state = {"persist": np.ascontiguousarray(rows), "steps_done": self.steps_done, "lanes": self.lanes,
+                 "n_persist": P, "records_crc": self._records_crc()}
+        if prog.design is not None:
+            state["net_bit_slots"] = self._canonical_slots()[0]
+        return state
 
     def load_state_dict(self, state):
         prog = self.program
@@ -694,28 +741,44 @@ class B200Engine(Executor):
         if state["n_persist"] == P and state.get("records_crc") == self._records_crc():
             full[:, :self.words] = state["persist"]              # same program: slot for slot
         else:
-            # another program of the same circuit: move the rows signal by signal
-            n_pin = len(prog.sig_kept)
-            if "signals" not in state or state["n_pin_signals"] != n_pin:
+            # another program of the same circuit: move the rows net bit by net bit
+            if "net_bit_slots" not in state or prog.design is None:
                 raise ValueError("checkpoint is for another netlist")
-            shared = prog.net_sig is not None and prog.design is not None and \
-                not np.array_equal(prog.net_sig, prog.design.net_sig)
-            if bool(state.get("shared_edge_detectors", False)) != bool(shared):
-                raise ValueError("checkpoint and engine differ in share_edge_detectors")
-            src_slot = np.full(n_pin, -1, dtype=np.int64)
-            src_slot[state["signals"]] = state["signal_slots"]
-            mine = np.asarray(prog.sig_slot[:n_pin], dtype=np.int64)
-            need = np.nonzero((mine >= 0) & (mine < P))[0]
-            missing = need[src_slot[need] < 0]
+            mine, sig = self._canonical_slots()
+            theirs = np.asarray(state["net_bit_slots"], dtype=np.int64)
+            if len(theirs) != len(mine):
+                raise ValueError("checkpoint is for another netlist")
+            need = np.nonzero(mine >= 0)[0]
+            missing = need[theirs[need] < 0]
             if len(missing):
-                raise ValueError("checkpoint lacks %d signals this engine keeps (e.g. signal %d): it was written with "
+                raise ValueError("checkpoint lacks %d net bits this engine keeps (e.g. bit %d): it was written with "
                                  "another keep= / observe= selection" % (len(missing), int(missing[0])))
-            full[mine[need], :self.words] = state["persist"][src_slot[need]]
-            for sig, shadow in prog.sig_shadow.items():          # 'prev' shadows hold the end-of-step value
-                if 0 <= shadow < P and sig < n_pin and src_slot[sig] >= 0:
-                    full[shadow, :self.words] = state["persist"][src_slot[sig]]
+            full[mine[need], :self.words] = state["persist"][theirs[need]]
+            for s_, shadow in prog.sig_shadow.items():           # 'prev' shadows hold the end-of-step value
+                if 0 <= shadow < P:
+                    hit = np.nonzero((sig == s_) & (theirs >= 0))[0]
+                    if len(hit):
+                        full[shadow, :self.words] = state["persist"][theirs[hit[0]]]
         self._plane[:P * self.stride] = self.rt.to_device(full.reshape(-1))
         self.steps_done = int(state["steps_done"])
+
+    def _unshare_edge_detectors(self):
+        """Rebuild this engine WITHOUT shared edge detectors, keeping all state: called when a caller pokes the
+        ``prevclock`` pin of one Register / Counter of a sharing group, which the shared bit cannot represent
+        (in the reference every primitive has its own ``prevclock`` global, simulator.py:100-127)."""
+        kw = dict(self._ctor_kwargs)
+        kw["share_edge_detectors"] = False
+        if self.mode == "serial" or kw.get("mode") == "serial":
+            kw["mode"] = "serial"
+        new = B200Engine(self.root, self.burst_size, self.map_pins, runtime=self.rt, **kw)
+        new.load_state_dict(self.state_dict())
+        toggle = self._toggle
+        self.close()
+        self.__dict__.update(new.__dict__)
+        new._d_records = None                                    # its graphs and buffers are ours now
+        if toggle is not None:
+            raise CircuitError("toggle counting and an individual prevclock poke in a shared group: rebuild the engine "
+                               "with share_edge_detectors=False first")
 
     def regions_skipped(self) -> int:
         """Serial mode: how many guarded regions the first warp jumped over so far (a sample of

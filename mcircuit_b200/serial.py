@@ -668,7 +668,7 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
             constants.append((base, design.pin_width[pin], int(desc.value)))
 
     prog = Program(
-        net_sig=ops.net_sig, design=design, records=stream, level_off=np.array([0, n_blocks], dtype=np.int32),
+        net_sig=ops.net_sig, shared_prev=set(ops.shared_prev), design=design, records=stream, level_off=np.array([0, n_blocks], dtype=np.int32),
         n_levels=1 if n_blocks else 0, has_latch=False, n_persist=n_persist, n_scratch=n_scratch,
         sig_slot=sig_slot, sig_shadow={}, sig_kept=kept, n_gates=int(is_gate.sum()), n_ops=n_ops,
         gate_words_bytes=gw_bytes, constants=constants, max_level_gates=n_ops, records_hinted=None, serial=True)

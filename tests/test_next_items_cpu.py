@@ -176,6 +176,50 @@ def test_checkpoint_resume_across_execution_modes(modes, back_edges):
         ora.step()
     for p in b.output_pins():
         assert np.array_equal(b.get_pin_state(p, lanes=True), ora.get_pin_state(p, lanes=True)), p
-    shared = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode="serial", keep="ports", share_edge_detectors=True)
-    with pytest.raises(ValueError):
-        shared.load_state_dict(snap)
+    # ... and across share_edge_detectors: checkpoints are keyed by net bit, members' prevclock nets resolve to the leader
+    for share_a, share_b in ((False, True), (True, False)):
+        a = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode=modes[0], keep="ports", share_edge_detectors=share_a)
+        ora = restate.RestatedJIT(root, 1, True, lanes=128)
+        for n in range(3):
+            a.set_pin_state(f"/l{n}_q0/out", 1)
+            ora.set_pin_state(f"/l{n}_q0/out", 1)
+        a.run(7)
+        b = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode=modes[1], keep="ports", share_edge_detectors=share_b)
+        b.load_state_dict(a.state_dict())
+        b.run(12)
+        for _ in range(19):
+            ora.step()
+        for p in b.output_pins() + ["/l1_q3/prevclock", "/p2/prevclock"]:
+            assert np.array_equal(b.get_pin_state(p, lanes=True), ora.get_pin_state(p, lanes=True)), (p, share_a, share_b)
+
+
+@pytest.mark.parametrize("mode", ["auto", "levels", "serial", "resident"])
+def test_poking_one_members_prevclock_unshares_the_engine(mode):
+    """Edge detectors are shared by default; the reference has one prevclock global per primitive
+    (simulator.py:100-127), so a poke of ONE member's prevclock rebuilds the engine unshared, state intact."""
+    root = circuits.lfsr_pipeline(MD, 3, 8, 6, taps=(7, 5, 1, 0))
+    eng = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode=mode)
+    ora = restate.RestatedJIT(root, 1, True, lanes=128)
+    assert eng.program.shared_prev
+    n_shared = eng.program.n_gates
+    rng = np.random.default_rng(3)
+    for n in range(3):
+        v = rng.integers(0, 2, size=128, dtype=np.uint64)
+        eng.set_pin_state(f"/l{n}_q0/out", v)
+        ora.set_pin_state(f"/l{n}_q0/out", v)
+    eng.run(5)
+    for _ in range(5):
+        ora.step()
+    assert eng.program.shared_prev                       # ordinary pokes and runs keep sharing
+    lanes_v = rng.integers(0, 2, size=128, dtype=np.uint64)
+    for sim in (eng, ora):
+        sim.set_pin_state("/l1_q4/prevclock", lanes_v)     # one register of the group, per lane
+        sim.set_pin_state("/p3/prevclock", 1)
+    assert not eng.program.shared_prev and eng.program.n_gates > n_shared and eng.steps_done == 5
+    for step in range(9):
+        eng.step()
+        ora.step()
+        for p in eng.output_pins() + ["/l1_q4/out", "/l1_q4/prevclock", "/l1_q5/prevclock", "/p3/out", "/p3/prevclock"]:
+            assert np.array_equal(eng.get_pin_state(p, lanes=True), ora.get_pin_state(p, lanes=True)), (step, p)
+    with pytest.raises(KeyError):
+        eng.set_pin_state("/nope/prevclock", 1)
