@@ -714,9 +714,14 @@ def run_ours(a):
                "ms_per_step": ems / a.steps,
                "host_link_GBps_per_gpu": (h2d + d2h) / (ems / a.steps * 1e-3) / 1e9,
                "host_link_GBps_all_gpus": world * (h2d + d2h) / (ems / a.steps * 1e-3) / 1e9,
-               "host_link_ceiling": traffic.get("host_copy_ceiling"),
+               "host_link_ceiling": (traffic.get("host_copy_ceiling") or {}).get(str(world)),
+               "host_link_ceiling_note": (traffic.get("host_copy_ceiling") or {}).get("what"),
                "api": "B200Engine.run_host(h_in, h_out) [tile-pipelined H2D / eval / D2H over the C ABI] "
                       "-> signature -> D2H (pinned host buffers)"}
+        ceil = e2e["host_link_ceiling"]
+        if ceil:
+            # both directions are in flight at once, so the platform's concurrent figure is the bound
+            e2e["host_link_fraction_of_ceiling"] = e2e["host_link_GBps_all_gpus"] / ceil["both_GBps"]
         assert np.array_equal(h_sig.numpy().view(np.uint64), signature_host), "e2e signature differs from resident run"
         # the downloaded planes really are the outputs: their popcounts are the signature
         local_sig = eng.rt.to_host_u64(eng.signature_run(sig))       # this rank's shard, not reduced
