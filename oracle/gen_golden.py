@@ -182,10 +182,26 @@ def schematic_cases():
     print("schematic.json:", len(out), "cases")
 
 
+def c4_gate_level_case():
+    """C4's shape at C4's own LFSR width and taps (32 bits, x^32 + x^22 + x^2 + x + 1) plus a 64-stage pipeline, built from
+    the gate-level master-slave flip-flops of examples/raw_counter.py, which the UNMODIFIED reference compiles and runs."""
+    return case_trace("c4_gate_level_lfsr32", "gate_level_lfsr", {"n_bits": 32, "taps": [31, 21, 1, 0], "stages": 64},
+                      [f"/q{i}/pin" for i in range(32)] + [f"/p{k}/pin" for k in range(64)] + ["/clk/out/pin"], 400,
+                      note="32-bit LFSR with C4's taps + 64-stage pipeline out of gate-level flip-flops; unmodified reference JIT")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     schematic_cases()
     if "--schematic-only" in sys.argv:
+        return
+    if "--c4-gate-level-only" in sys.argv:                 # add / refresh that one case, keep the rest of traces.json
+        path = os.path.join(OUT, "traces.json")
+        cases = [c for c in json.load(open(path)) if c["name"] != "c4_gate_level_lfsr32"]
+        cases.append(c4_gate_level_case())
+        with open(path, "w") as f:
+            json.dump(cases, f, separators=(",", ":"))
+        print("traces.json:", len(cases), "cases")
         return
     cases = []
     # --- the reference's three examples (SURVEY section 4) ---------------------------------
@@ -205,6 +221,7 @@ def main():
     cases.append(case_trace("c4_gate_level_lfsr", "gate_level_lfsr", {"n_bits": 8, "taps": [7, 5, 4, 3], "stages": 4},
                             [f"/q{i}/pin" for i in range(8)] + [f"/p{k}/pin" for k in range(4)] + ["/clk/out/pin"], 200,
                             note="LFSR + pipeline out of the master-slave flip-flops of examples/raw_counter.py"))
+    cases.append(c4_gate_level_case())
     # --- random circuits: every primitive the reference can compile, feedback, hierarchy -------
     for seed in range(40):
         made, probes = circuits.random_circuit(D, seed, n_nodes=18)

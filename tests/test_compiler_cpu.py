@@ -10,7 +10,9 @@ from _helpers import (build, compare_engine_to_oracle, golden, lane_trick_planes
 from mcircuit_b200 import circuits, compiler
 from mcircuit_b200.engine import B200Engine
 
-TRACES = golden("traces.json")
+HEAVY = ("c4_gate_level_lfsr32",)          # 97 probes x 400 steps: in full on the GPU and on the oracles, shortened on the numpy test double
+ALL_TRACES = golden("traces.json")
+TRACES = [c for c in ALL_TRACES if c["name"] not in HEAVY]
 
 
 def engine_factory(mode="resident", keep="all", map_pins=True, **kw):
