@@ -405,7 +405,7 @@ def run_configs(a, dev, world, rank, jits):
 
     # ---- C1: examples/counter.py, 1,000 cycles = 2,000 steps, single instance ---------------------------
     root = circuits.counter_circuit()
-    eng = B200Engine(root, 501, True, lanes=64, device=dev.index, mode="serial")
+    eng = B200Engine(root, 501, True, lanes=64, device=dev.index)
     ora = restate.RestatedJIT(root, 501, True)
     eng.run(2000)
     for _ in range(2000):
@@ -417,7 +417,7 @@ def run_configs(a, dev, world, rank, jits):
     ok = ok and all(eng.get_pin_state(p) == ora.get_pin_state(p) for p in pins)
     ms = timed(lambda: eng.run(2000))
     e = entry("C1 examples/counter.py clocked counter, 1,000 cycles (2,000 steps), single instance", eng, 64, 2000, ms,
-              "latency (one warp walks 4 micro-ops per step; nothing to parallelise in a single instance)",
+              "latency (one warp walks 4 micro-ops per step; nothing to parallelise in a single instance; mode chosen: %s)" % eng.mode,
               {"bit_exact": all_ok(ok), "against": "oracle/restate.py after 2,000 steps and after burst() (502 more)", "pins": list(pins)},
               False, {"lanes_note": "the reference's single instance is lane 0 of one 64-lane word; replicas only at N > 1"})
     if rank == 0:
@@ -429,7 +429,7 @@ def run_configs(a, dev, world, rank, jits):
     # ---- C2: 32-bit ripple-carry adder, 2^20 vectors, one combinational step -----------------------------
     lanes = 1 << 20
     root = circuits.ripple_adder(nbits=32)
-    eng = B200Engine(root, 1, True, lanes=lanes, device=dev.index, mode="serial", keep="ports", lane_word_offset=rank * (lanes // 64))
+    eng = B200Engine(root, 1, True, lanes=lanes, device=dev.index, keep="ports", lane_word_offset=rank * (lanes // 64))
     eng.randomize_inputs()
     eng.step()
     planes = {p: eng.get_pin_planes(p)[0] for p in eng.input_pins() + eng.output_pins()}

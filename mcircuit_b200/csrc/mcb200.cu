@@ -1101,6 +1101,22 @@ __device__ __forceinline__ W stream_operand(uint32_t kind, uint32_t field, const
     }
 }
 
+// The same, branch-free for the operand kinds that live in registers or shared memory: one load from an address
+// that is valid whatever the kind, then selects.  Generic records decode three operands each; as three jump tables
+// they cost three indirect branches per record on a single warp.
+template <typename W, bool UNIFIED>
+__device__ __forceinline__ W stream_operand_bf(uint32_t kind, uint32_t field, const W *rows, const W *stash,
+                                               const GlobalCols<W, UNIFIED> &cols, W acc, W greg, bool active) {
+    const bool in_smem = kind == TK_RING || kind == TK_STASH;
+    const W *p = (kind == TK_STASH ? stash : rows) + (in_smem ? field : 0u) * STR_NT;
+    W x = *p;
+    if (kind == TK_LATE) x = active ? cols.ld(field) : (W)0;        // rare; uniform
+    x = kind == TK_ACC ? acc : x;
+    x = kind == TK_GREG ? greg : x;
+    x = kind == TK_NONE ? (W)0 : x;
+    return x;
+}
+
 // N enabled registers in a row: out = G ? d : out.  `rows` points at the ring row of the first unit (row u
 // holds the old value of unit u), `slots` at its slot (= the slot to store to); every stage takes the
 // previous stage's NEW value (the reference's in-place order) - pure register forwarding.  Straight-line:
@@ -1283,12 +1299,13 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
                 } else if (kind == SEG_GUARD) {
                     guard_rec = f;
                 } else {
+#pragma unroll 2
                     for (int u = 0; u < n; ++u) {
                         const uint4 r = recs[f + u];
                         const uint32_t flags = r.x >> 24;
-                        const W a = stream_operand<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
-                        const W bb = stream_operand<W, UNIFIED>((r.y >> 27) & 7u, r.y & STR_M24, rows, stash, cols, acc, greg, active);
-                        const W c = stream_operand<W, UNIFIED>((r.z >> 24) & 7u, r.z & STR_M24, rows, stash, cols, acc, greg, active);
+                        const W a = stream_operand_bf<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
+                        const W bb = stream_operand_bf<W, UNIFIED>((r.y >> 27) & 7u, r.y & STR_M24, rows, stash, cols, acc, greg, active);
+                        const W c = stream_operand_bf<W, UNIFIED>((r.z >> 24) & 7u, r.z & STR_M24, rows, stash, cols, acc, greg, active);
                         const W res = apply_op_w<W>((flags & 15u) | ((flags & 16u) << 3), a, bb, c);
                         if ((flags & 32u) && active) cols.st(r.w & STR_M24, res);
                         const uint32_t so = r.w >> 24;

@@ -105,9 +105,23 @@ class B200Engine(Executor):
                     # number of steps, rows staged by TMA, idle clock phases skipped)
                     from . import serial
                     try:
-                        program = serial.compile_serial(design, keep=keep, observe=observe,
-                                                        share_edge_detectors=share_edge_detectors, guard=serial_guard,
-                                                        adder_prefix=adder_prefix, **(serial_options or {}))
+                        stream = serial.compile_serial(design, keep=keep, observe=observe,
+                                                       share_edge_detectors=share_edge_detectors, guard=serial_guard,
+                                                       adder_prefix=adder_prefix, **(serial_options or {}))
+                        # ... but only when the stream is made of what K3 is good at - enabled-register chains and
+                        # pipeline stages (consecutive rows in few TMA boxes, straight-line code).  A stream of generic
+                        # records with scattered operands costs a TMA box per operand and ~45 instructions per record:
+                        # the resident kernel on the levelized batches is 1.5 - 5 x faster there
+                        # (profiles/r02_modes_compare.jsonl)
+                        info = stream.serial_info
+                        n_rec = max(1, info["records"])
+                        registers = info["mux_chain_units"] + 2 * info["xor_mux_units"] >= 0.5 * n_rec
+                        # ... or, at large lane counts (where the resident kernel's time grows with the lanes and the
+                        # stream's does not), a stream whose operands are mostly forwarded through registers / stash
+                        forwarded = (self.words >= 4096 and info["tma_boxes"] <= 0.25 * n_rec and
+                                     info["late_operands"] <= 0.05 * n_rec)
+                        if registers or forwarded:
+                            program = stream
                     except compiler.CircuitError:
                         pass                                     # more than 2^24 slots: stay with the level program
         if getattr(program, "serial", False):
@@ -163,9 +177,14 @@ class B200Engine(Executor):
 
         # ---- execution mode -------------------------------------------------------------------
         if mode == "auto":
-            # per-level launches pay off only when one level of one tile keeps the whole GPU
-            # busy for longer than a launch gap; otherwise one resident launch walks everything
-            mode = "levels" if avg_level * self.tile_words >= (1 << 19) else "resident"
+            # per-level launches cost a launch gap per level (~3.3 us) or the level's bytes at HBM speed; one resident
+            # launch walks batches of 8 records at one dependent memory round trip each (~0.75 us) or its bytes at a
+            # lower rate.  Pick the smaller estimate (checked against profiles/r02_modes_compare.jsonl: a 20k-gate,
+            # 40-level DAG wants levels even at 2^16 lanes, a 1.4k-gate multiplier or a gate-level LFSR wants resident)
+            tw = float(self.tile_words)
+            t_levels = program.n_levels * max(3.3e-6, avg_level * tw * 24.0 / 6.0e12)
+            t_resident = max((program.n_ops / 8.0 + program.n_levels) * 0.75e-6, program.n_ops * tw * 24.0 / 4.0e12)
+            mode = "levels" if (t_levels <= t_resident or self.trash_slot >= compiler.IN2_LIMIT) else "resident"
         if mode not in ("levels", "levels_grouped", "resident", "persistent", "serial"):
             raise ValueError("mode must be 'auto', 'levels', 'levels_grouped', 'resident', 'serial' or 'persistent'")
         self.mode = mode
