@@ -477,12 +477,14 @@ static int launch_level_tma(const uint4 *recs, int n, const View &v, cudaStream_
     const size_t smem = LT_HEAD_BYTES + (size_t)LT_STAGES * 4 * LT_ROW_BYTES;
     int grid = sm_count() * 2;
     if (grid > n) grid = n;
-    static bool attr_set[2] = {false, false};
+    static std::atomic<bool> attr_set[2][64];                // per device
     const int pdl = g_tune.level_pdl ? 1 : 0;
-    if (!attr_set[pdl]) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (!attr_set[pdl][dev & 63].load(std::memory_order_acquire)) {
         if (pdl) CUDA_TRY(cudaFuncSetAttribute(k_eval_level_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else CUDA_TRY(cudaFuncSetAttribute(k_eval_level_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[pdl] = true;
+        attr_set[pdl][dev & 63].store(true, std::memory_order_release);
     }
     if (pdl) {
         cudaLaunchConfig_t cfg = {};
@@ -1370,14 +1372,30 @@ static unsigned long long g_tmap_tick = 0;
 // 2 planes x 6 box heights, 128 bytes each, in device memory; cached per geometry
 static int stream_tensor_maps(const View &v, long long n_slots, int word_bytes, long long ext_cols, bool unified,
                               const unsigned char **out) {
+    // the last geometry used (the common case: the same engine stepping): no formatting, no hashing
+    struct Last { const void *p, *s; long long ps, ss, ns, ec; unsigned np; int wb; const unsigned char *maps; };
+    static thread_local Last last = {nullptr, nullptr, 0, 0, 0, 0, 0, 0, nullptr};
+    static thread_local unsigned long long last_epoch = 0;
+    static std::atomic<unsigned long long> epoch{1};         // bumped whenever entries are evicted
+    if (last.maps && last_epoch == epoch.load(std::memory_order_acquire) && last.p == v.persist &&
+        last.s == v.scratch_biased && last.ps == v.pstride && last.ss == v.sstride && last.ns == n_slots &&
+        last.ec == ext_cols && last.np == v.n_persist && last.wb == word_bytes) {
+        *out = last.maps;
+        return 0;
+    }
     char key[256];
     snprintf(key, sizeof key, "%p|%lld|%p|%lld|%u|%lld|%d|%lld", (void *)v.persist, v.pstride, (void *)v.scratch_biased,
              v.sstride, v.n_persist, n_slots, word_bytes, ext_cols);
     std::lock_guard<std::mutex> lock(g_tmap_mu);
+    auto remember = [&](const unsigned char *maps) {
+        last = Last{v.persist, v.scratch_biased, v.pstride, v.sstride, n_slots, ext_cols, v.n_persist, word_bytes, maps};
+        last_epoch = epoch.load(std::memory_order_acquire);
+    };
     auto it = g_tmaps.find(key);
     if (it != g_tmaps.end()) {
         it->second.last_use = ++g_tmap_tick;
         *out = it->second.d_maps;
+        remember(*out);
         return 0;
     }
     PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
@@ -1423,12 +1441,14 @@ static int stream_tensor_maps(const View &v, long long n_slots, int word_bytes, 
             cudaFree(g_tmaps[order[i].second].d_maps);
             g_tmaps.erase(order[i].second);
         }
+        epoch.fetch_add(1, std::memory_order_acq_rel);
     }
     unsigned char *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, sizeof maps));
     CUDA_TRY(cudaMemcpy(d, maps, sizeof maps, cudaMemcpyHostToDevice));
     g_tmaps[key] = TmapEntry{d, ++g_tmap_tick};
     *out = d;
+    remember(d);
     return 0;
 }
 
@@ -1464,7 +1484,13 @@ static int launch_stream_w(const uint32_t *stream, int n_blocks, int ring_rows, 
     if (groups < 2) return fail(MCB_ERR_ARG, "shared memory too small for the stream ring");
     const size_t smem = fixed + (size_t)groups * group_bytes;
     auto kern = unified ? k_run_stream<W, true> : k_run_stream<W, false>;
-    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // the attribute is per device and per instantiation (W is a template parameter of this function)
+    static std::atomic<size_t> smem_set[2][64];
+    std::atomic<size_t> &done = smem_set[unified ? 1 : 0][dev & 63];
+    if (done.load(std::memory_order_acquire) < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        done.store(smem, std::memory_order_release);
+    }
     kern<<<(unsigned)grid, 32 * (STR_CONSUMER_WARPS + 1), smem, s>>>(stream, n_blocks, v, steps, cols, d_maps, d_skipped,
                                                                      groups, ring_rows);
     LAUNCH_CHECK("k_run_stream");

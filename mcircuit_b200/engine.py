@@ -147,8 +147,16 @@ class B200Engine(Executor):
         # ---- tiling ------------------------------------------------------------------------------
         persist_bytes = P * self.stride * 8
         avg_level = program.n_ops / max(1, program.n_levels)
-        wide = (mode in ("levels", "levels_grouped") or
-                (mode == "auto" and avg_level * min(self.words, DEFAULT_TILE_WORDS) >= (1 << 19)))
+        if mode == "auto":
+            # per-level launches cost a launch gap per level (~3.3 us) or the level's bytes at HBM speed; one resident
+            # launch walks batches of 8 records at one dependent memory round trip each (~0.75 us) or its bytes at a
+            # lower rate.  Pick the smaller estimate (checked against profiles/r02_modes_compare.jsonl: a 20k-gate,
+            # 40-level DAG wants levels even at 2^16 lanes, a 1.4k-gate multiplier or a gate-level LFSR wants resident)
+            tw = float(min(self.words, DEFAULT_TILE_WORDS))
+            t_levels = program.n_levels * max(3.3e-6, avg_level * tw * 24.0 / 6.0e12)
+            t_resident = max((program.n_ops / 8.0 + program.n_levels) * 0.75e-6, program.n_ops * tw * 24.0 / 4.0e12)
+            mode = "levels" if (t_levels <= t_resident or self.trash_slot >= compiler.IN2_LIMIT) else "resident"
+        wide = mode in ("levels", "levels_grouped")
         if tile_words is None:
             fits = (P + S) * self.stride * 8 <= budget
             # a level launch should carry as many gate-words as a 5,000-gate level of a 512-word tile does
@@ -176,15 +184,6 @@ class B200Engine(Executor):
                 % (P, self.stride, S, tile_words))
 
         # ---- execution mode -------------------------------------------------------------------
-        if mode == "auto":
-            # per-level launches cost a launch gap per level (~3.3 us) or the level's bytes at HBM speed; one resident
-            # launch walks batches of 8 records at one dependent memory round trip each (~0.75 us) or its bytes at a
-            # lower rate.  Pick the smaller estimate (checked against profiles/r02_modes_compare.jsonl: a 20k-gate,
-            # 40-level DAG wants levels even at 2^16 lanes, a 1.4k-gate multiplier or a gate-level LFSR wants resident)
-            tw = float(self.tile_words)
-            t_levels = program.n_levels * max(3.3e-6, avg_level * tw * 24.0 / 6.0e12)
-            t_resident = max((program.n_ops / 8.0 + program.n_levels) * 0.75e-6, program.n_ops * tw * 24.0 / 4.0e12)
-            mode = "levels" if (t_levels <= t_resident or self.trash_slot >= compiler.IN2_LIMIT) else "resident"
         if mode not in ("levels", "levels_grouped", "resident", "persistent", "serial"):
             raise ValueError("mode must be 'auto', 'levels', 'levels_grouped', 'resident', 'serial' or 'persistent'")
         self.mode = mode

@@ -223,3 +223,15 @@ def test_poking_one_members_prevclock_unshares_the_engine(mode):
             assert np.array_equal(eng.get_pin_state(p, lanes=True), ora.get_pin_state(p, lanes=True)), (step, p)
     with pytest.raises(KeyError):
         eng.set_pin_state("/nope/prevclock", 1)
+
+
+def test_auto_mode_policy():
+    """mode='auto' (measured in profiles/r02_modes_compare.jsonl): register-dominated sequential designs run on the
+    stream kernel, small gate-level designs on the resident kernel, wide netlists level by level."""
+    def mode_of(root, lanes):
+        return B200Engine(root, 1, True, lanes=lanes, runtime=CpuRuntime(), keep="ports").mode
+    assert mode_of(circuits.lfsr_pipeline(MD, 8, 16, 60, taps=(15, 13, 12, 10)), 64 * 16) == "serial"
+    assert mode_of(circuits.counter_circuit(MD), 64) == "resident"
+    assert mode_of(circuits.array_multiplier(MD, 8), 64 * 16) == "resident"
+    assert mode_of(circuits.gate_level_lfsr(MD), 64 * 16) == "resident"
+    assert mode_of(circuits.random_dag(MD, n_gates=6000, depth=12, n_inputs=64, seed=5), 64 * 64) == "levels"
