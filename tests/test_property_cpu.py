@@ -75,3 +75,42 @@ def test_c_oracle_equals_numpy_oracle(seed, n_nodes, max_width, map_pins):
         b.step()
         for p in probes:
             assert np.array_equal(a.get_pin_state(p, lanes=True), b.get_pin_state(p, lanes=True)), (step, p)
+
+
+@settings(max_examples=36, deadline=None, derandomize=True, suppress_health_check=[HealthCheck.too_slow])
+@given(seed=st.integers(0, 10**6), n_nodes=st.integers(2, 40), max_width=st.sampled_from([1, 2, 5, 8, 33, 64]),
+       feedback=st.booleans(), hierarchy=st.booleans(), map_pins=st.booleans(), keep=st.sampled_from(["all", "ports"]),
+       share=st.booleans(), guard=st.booleans(), patterns=st.booleans(), stash=st.booleans(), ring=st.booleans(),
+       prefix=st.booleans(), model=st.sampled_from(["early", "late"]), cta_cols=st.sampled_from([1, 2, 128]),
+       chunks=st.lists(st.integers(1, 40), min_size=1, max_size=4))
+def test_serial_stream_equals_oracle(seed, n_nodes, max_width, feedback, hierarchy, map_pins, keep, share, guard, patterns,
+                                     stash, ring, prefix, model, cta_cols, chunks):
+    """The stream program (K3) under the test double's producer / consumer model - staged rows fetched as early as the
+    kernel may with only fenced stores visible, or as late as possible - for ANY circuit, ANY combination of the stream's
+    optimisations and ANY split of the run into launches."""
+    root, probes = circuits.random_circuit(MD, seed=seed, n_nodes=n_nodes, max_width=max_width, feedback=feedback,
+                                           hierarchy=hierarchy, primitives=ALL_PRIMS + ("Register", "Counter"))
+    lanes = 64 * 3
+    rt = CpuRuntime()
+    rt.serial_fetch_model, rt.serial_cta_cols = model, cta_cols
+    ora = restate.RestatedJIT(root, 2, map_pins, lanes=lanes)
+    eng = B200Engine(root, 2, map_pins, lanes=lanes, runtime=rt, keep=keep, mode="serial", share_edge_detectors=share,
+                     serial_guard=guard, adder_prefix=prefix, serial_options=dict(patterns=patterns, stash=stash, ring=ring))
+    rng = np.random.default_rng(seed)
+    d = eng.program.design
+    for p in ("/in0/pin", "/in1/pin"):
+        w = d.pin_width[d.find_pin(p)]
+        v = rng.integers(0, (1 << w) - 1, size=lanes, dtype=np.uint64, endpoint=True)
+        ora.set_pin_state(p, v)
+        eng.set_pin_state(p, v)
+    for n in chunks:
+        eng.run(n)                                        # ONE launch of n steps: the producer runs ahead across steps
+        for _ in range(n):
+            ora.step()
+        for p in probes:
+            try:
+                got = eng.get_pin_state(p, lanes=True)
+            except compiler.PinNotObservable:
+                assert keep == "ports"
+                continue
+            assert np.array_equal(got, ora.get_pin_state(p, lanes=True)), (n, p)
