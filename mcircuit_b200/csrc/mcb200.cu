@@ -362,14 +362,14 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t by
 // K1t: one level with the per-level signal state staged in shared memory by TMA bulk copies.
 // CTA = 1 producer warp + 4 consumer warps, persistent over the level's records (record i of CTA c
 // = c + i * gridDim.x).  Producer: per record, the 16-byte record goes into the stage header and
-// every fan-in row of the lane tile (<= 4 KB) is one cp.async.bulk into the stage, completion on
-// the stage's `full` mbarrier.  Consumers: 128 threads x 32 bytes cover a row; LOP3 on four words,
-// result into the stage's output buffer, fence.proxy.async, and every warp sends its own kilobyte
-// of the output row back with one cp.async.bulk shared -> global (bulk_group), so no CTA-wide
-// barrier is needed.  Six stages, two CTAs per SM: ~100 KB of rows in flight per SM without a
-// single LDG on the record -> address -> row chain that stalls K1.
+// the first two fan-in rows of the lane tile (<= 4 KB each) are one cp.async.bulk each into the
+// stage, completion on the stage's `full` mbarrier.  Consumers: 128 threads x 32 bytes cover a row;
+// LOP3 on four words out of shared memory, the result straight to global memory.  Twelve stages,
+// two CTAs per SM: ~190 KB of rows in flight per SM without a single LDG on the record -> address
+// -> row chain that stalls K1.  Measured 1.7 x SLOWER than K1 on C5 (profiles/r02_k1t_vs_k1.md):
+// opt-in (`level_tma` tuning).
 // ------------------------------------------------------------------------------------------
-#define LT_STAGES 6
+#define LT_STAGES 12
 #define LT_ROW_BYTES 4096
 #define LT_HEAD_BYTES 1024
 struct LtSmem {
@@ -384,7 +384,6 @@ k_eval_level_tma(const uint4 *__restrict__ recs, int n_recs, View v, uint32_t ro
     extern __shared__ __align__(128) unsigned char lt_smem[];
     LtSmem *sh = reinterpret_cast<LtSmem *>(lt_smem);
     unsigned char *in_base = lt_smem + LT_HEAD_BYTES;
-    unsigned char *out_base = in_base + LT_STAGES * 3 * LT_ROW_BYTES;
     if (PDL) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
@@ -397,7 +396,7 @@ k_eval_level_tma(const uint4 *__restrict__ recs, int n_recs, View v, uint32_t ro
     __syncthreads();
     const int first = blockIdx.x, stride = gridDim.x;
     if (warp == 4) {
-        // ---- producer ----
+        // ---- producer: the two first fan-in rows of every record, one bulk copy each ----
         uint32_t s = 0, ph = 1;
         bool waited = !PDL;
         for (int i = first; i < n_recs; i += stride) {
@@ -409,32 +408,28 @@ k_eval_level_tma(const uint4 *__restrict__ recs, int n_recs, View v, uint32_t ro
             mbar_wait(&sh->empty[s], ph);
             if (lane == 0) {
                 const uint32_t op = r.x & 0x7fu;
-                const uint32_t arity = op == MCB_OP_NOP ? 0u : (op == MCB_OP_BUF ? 1u : (op >= MCB_OP_MUX ? 3u : 2u));
+                const uint32_t n_rows = op == MCB_OP_NOP ? 0u : (op == MCB_OP_BUF ? 1u : 2u);
                 sh->hdr[s] = r;
-                mbar_expect_tx(&sh->full[s], arity * row_bytes);
-                unsigned char *dst = in_base + s * 3 * LT_ROW_BYTES;
-                if (arity >= 1) bulk_g2s(dst, row(v, r.y), row_bytes, &sh->full[s]);
-                if (arity >= 2) bulk_g2s(dst + LT_ROW_BYTES, row(v, r.z), row_bytes, &sh->full[s]);
-                if (arity >= 3) bulk_g2s(dst + 2 * LT_ROW_BYTES, row(v, r.x >> 8), row_bytes, &sh->full[s]);
+                mbar_expect_tx(&sh->full[s], n_rows * row_bytes);
+                unsigned char *dst = in_base + s * 2 * LT_ROW_BYTES;
+                if (n_rows >= 1) bulk_g2s(dst, row(v, r.y), row_bytes, &sh->full[s]);
+                if (n_rows >= 2) bulk_g2s(dst + LT_ROW_BYTES, row(v, r.z), row_bytes, &sh->full[s]);
             }
             if (++s == LT_STAGES) { s = 0; ph ^= 1u; }
         }
         if (!waited) asm volatile("griddepcontrol.wait;" ::: "memory");
         return;
     }
-    // ---- consumers ----
+    // ---- consumers: LOP3 out of shared memory, the result straight to global memory (32 bytes per thread) ----
     if (PDL) asm volatile("griddepcontrol.wait;" ::: "memory");      // before the first store of this level
     const uint32_t my = tid * 32u;
     const bool has0 = my < row_bytes, has1 = my + 16u < row_bytes;
-    const uint32_t lo = warp * 1024u;
-    const uint32_t part = lo < row_bytes ? (row_bytes - lo < 1024u ? row_bytes - lo : 1024u) : 0u;
     uint32_t s = 0, ph = 0;
     for (int i = first; i < n_recs; i += stride) {
         mbar_wait(&sh->full[s], ph);
         const uint4 r = sh->hdr[s];
         const uint32_t op = r.x & 0xffu, base = op & 0x7fu;
-        const unsigned char *in = in_base + s * 3 * LT_ROW_BYTES + my;
-        unsigned char *out = out_base + s * LT_ROW_BYTES;
+        const unsigned char *in = in_base + s * 2 * LT_ROW_BYTES + my;
         if (base != MCB_OP_NOP && has0) {
             ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(in), a1 = make_ulonglong2(0, 0);
             ulonglong2 b0 = make_ulonglong2(0, 0), b1 = b0, c0 = b0, c1 = b0;
@@ -443,38 +438,29 @@ k_eval_level_tma(const uint4 *__restrict__ recs, int n_recs, View v, uint32_t ro
                 b0 = *reinterpret_cast<const ulonglong2 *>(in + LT_ROW_BYTES);
                 if (has1) b1 = *reinterpret_cast<const ulonglong2 *>(in + LT_ROW_BYTES + 16);
             }
-            if (base >= MCB_OP_MUX) {
-                c0 = *reinterpret_cast<const ulonglong2 *>(in + 2 * LT_ROW_BYTES);
-                if (has1) c1 = *reinterpret_cast<const ulonglong2 *>(in + 2 * LT_ROW_BYTES + 16);
+            if (base >= MCB_OP_MUX) {                   // the third operand of a 3-input micro-op: an ordinary load
+                const unsigned char *cr = reinterpret_cast<const unsigned char *>(row(v, r.x >> 8)) + my;
+                c0 = ld_state2<1>(reinterpret_cast<const uint64_t *>(cr));
+                if (has1) c1 = ld_state2<1>(reinterpret_cast<const uint64_t *>(cr + 16));
             }
             ulonglong2 o0, o1;
             o0.x = apply_op(op, a0.x, b0.x, c0.x);
             o0.y = apply_op(op, a0.y, b0.y, c0.y);
             o1.x = apply_op(op, a1.x, b1.x, c1.x);
             o1.y = apply_op(op, a1.y, b1.y, c1.y);
-            *reinterpret_cast<ulonglong2 *>(out + my) = o0;
-            if (has1) *reinterpret_cast<ulonglong2 *>(out + my + 16) = o1;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stores above, seen by the bulk copy below
-        __syncwarp();
-        if (lane == 0) {
-            mbar_arrive(&sh->empty[s]);                 // this warp is done with the stage's fan-in rows
-            if (part && base != MCB_OP_NOP) {
-                bulk_s2g(reinterpret_cast<unsigned char *>(row(v, r.w)) + lo, out + lo, part);
-                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                // the output buffer of this stage is written again LT_STAGES records from now
-                asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(LT_STAGES - 1) : "memory");
-            }
+            unsigned char *out = reinterpret_cast<unsigned char *>(row(v, r.w)) + my;
+            st_state2(reinterpret_cast<uint64_t *>(out), o0);
+            if (has1) st_state2(reinterpret_cast<uint64_t *>(out + 16), o1);
         }
         __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->empty[s]);      // this warp is done with the stage's fan-in rows
         if (++s == LT_STAGES) { s = 0; ph ^= 1u; }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 static int launch_level_tma(const uint4 *recs, int n, const View &v, cudaStream_t s) {
     const uint32_t row_bytes = (uint32_t)((v.n_words + 1) / 2 * 2 * 8);
-    const size_t smem = LT_HEAD_BYTES + (size_t)LT_STAGES * 4 * LT_ROW_BYTES;
+    const size_t smem = LT_HEAD_BYTES + (size_t)LT_STAGES * 2 * LT_ROW_BYTES;
     int grid = sm_count() * 2;
     if (grid > n) grid = n;
     static std::atomic<bool> attr_set[2][64];                // per device
