@@ -504,6 +504,8 @@ def run_configs(a, dev, world, rank, jits):
     probes = ["/pipe_out/pin"] + ["/tap%d/pin" % n for n in range(0, 256, 15)]
     got = eng.sample_planes(probes, cols)
     ok = all(np.array_equal(got[k], sim.planes(p)[0]) for k, p in enumerate(probes))
+    ones = float(np.unpackbits(got.view(np.uint8)).mean())       # the end state is alive, not a comparison of zeros
+    ok = ok and 0.4 < ones < 0.6
     full = steps == 200_000
     e = entry("C4 256 LFSRs + 1,000-register pipeline, %s clock cycles (%d steps)%s, 2^20 lanes, state resident"
               % ("{:,}".format(steps // 2), steps, " = the named size" if full else " of the 10^5 named"), eng, lanes, steps, ms,
@@ -512,6 +514,7 @@ def run_configs(a, dev, world, rank, jits):
               "clock's falling phase is the identity on every register)",
               {"bit_exact": all_ok(ok), "against": "oracle/mcref.c run for the same %d steps on 8 sampled lane words (512 lanes), "
                                                    "pipe_out and 18 LFSR taps" % steps,
+               "ones_fraction_of_the_compared_words": ones,
                "register_note": "Register parity is unpinned by the reference (its emitter does not compile, SURVEY Q3)"}, True,
               {"launches": int(launches), "regions_skipped_by_cta0": eng.regions_skipped(),
                "micro_ops_note": "gates counts the micro-ops executed with shared clock edge detectors (10,707); the unshared "

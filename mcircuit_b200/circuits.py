@@ -317,22 +317,32 @@ def array_multiplier(M=_own, n=64, width=1):
 
 
 # ---- C4: LFSRs + register pipeline -----------------------------------------------------------------------
-def lfsr_pipeline(M=_own, n_lfsr=256, lfsr_bits=32, stages=1000, taps=(31, 21, 1, 0)):
-    """``n_lfsr`` Fibonacci LFSRs of ``lfsr_bits`` ``Register(1)`` each (feedback =
-    XOR of the tap outputs into stage 0), one ``Clock``; a pipeline of ``stages``
-    ``Register(1)``: stage k data = XOR(stage k-1 out, lfsr[k % n_lfsr].q0).
-    Seeds go in through ``set_pin_state('/l{n}_q{b}/out', ...)``; observation ports
-    /tap{n}/pin (q0 of each LFSR) and /pipe_out/pin."""
+def lfsr_pipeline(M=_own, n_lfsr=256, lfsr_bits=32, stages=1000, taps=(31, 21, 0), couple=True):
+    """``n_lfsr`` feedback shift registers of ``lfsr_bits`` ``Register(1)`` each (feedback = XOR of the tap
+    outputs into stage 0), one ``Clock``; a pipeline of ``stages`` ``Register(1)``: stage k data =
+    XOR(stage k-1 out, row[k % n_lfsr].q0).
+
+    The reference evaluates primitives one after another in place, sources first, and a ``Register`` is
+    not double-buffered (simulator.py:115-127), so a directly chained register row FALLS THROUGH on the
+    rising edge: q1..q31 all take q0's old value, and a feedback of an even number of taps is then 0 -
+    an uncoupled row with four taps is all-zero after three steps, which would make every long-run
+    comparison a comparison of zeros.  ``couple=True`` (default) therefore adds one more feedback input,
+    q0 of the NEXT row (the last row takes row 0's), and the default has three own taps: row n evolves as
+    q0 <- q0 ^ q0[next row], a 256-cell linear automaton per lane that never settles (checked for 2 x 10^5
+    steps by the C4 tests).  Same micro-op count as the uncoupled four-tap row.
+    Seeds go in through ``set_pin_state('/l{n}_q{b}/out', ...)``; observation ports /tap{n}/pin (q0 of each
+    row) and /pipe_out/pin."""
     top = M.Composite()
     clk = M.Clock()
     reg = M.Register(1)
     eout = M.ExposedPin(M.ExposedPin.OUT)
     top.add_child("clk", clk)
     taps = [t for t in taps if t < lfsr_bits]
+    n_fb = max(len(taps) + (1 if couple and n_lfsr > 1 else 0), 1)
     for n in range(n_lfsr):
         for b in range(lfsr_bits):
             top.add_child(f"l{n}_q{b}", reg)
-        top.add_child(f"l{n}_fb", M.Gate(M.Gate.XOR, 1, max(len(taps), 1)))
+        top.add_child(f"l{n}_fb", M.Gate(M.Gate.XOR, 1, n_fb))
         top.add_child(f"tap{n}", eout)
     for k in range(stages):
         top.add_child(f"p{k}", reg)
@@ -345,6 +355,8 @@ def lfsr_pipeline(M=_own, n_lfsr=256, lfsr_bits=32, stages=1000, taps=(31, 21, 1
                 top.connect(f"l{n}_q{b - 1}", "out", f"l{n}_q{b}", "data")
         for i, t in enumerate(taps):
             top.connect(f"l{n}_q{t}", "out", f"l{n}_fb", f"in{i}")
+        if couple and n_lfsr > 1:
+            top.connect(f"l{(n + 1) % n_lfsr}_q0", "out", f"l{n}_fb", f"in{len(taps)}")
         top.connect(f"l{n}_fb", "out", f"l{n}_q0", "data")
         top.connect(f"l{n}_q0", "out", f"tap{n}", "")
     for k in range(stages):

@@ -41,8 +41,15 @@ def _worker(rank, world, port, total_lanes, out_dir):
         clk.engine.enable_toggle_counts(["/clk/out"])
         clk.run(6)
         tg = clk.toggle_counts()
-        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), pc=pc, cs=cs, tg=tg,
-                 lanes=sh.engine.lanes, off=sh.engine.lane_word_offset)
+        # C4's shape through the stream kernel's program (mode='serial'): per-rank seeds come from the counter-based
+        # stimulus at the rank's GLOBAL lane words, signatures are reduced over the ranks
+        seq = circuits.lfsr_pipeline(n_lfsr=4, lfsr_bits=8, stages=24, taps=(7, 5, 1, 0))
+        ser = ShardedEngine(seq, total_lanes, 1, True, runtime=CpuRuntime(), keep="ports", mode="serial")
+        ser.randomize_inputs(["/l%d_q%d/out" % (n, b) for n in range(4) for b in (0, 3)])
+        ser.run(21)
+        spc, scs = ser.signature()
+        np.savez(os.path.join(out_dir, "rank%d.npz" % rank), pc=pc, cs=cs, tg=tg, spc=spc, scs=scs,
+                 smode=ser.engine.mode, lanes=sh.engine.lanes, off=sh.engine.lane_word_offset)
     finally:
         dist.destroy_process_group()
 
@@ -62,9 +69,16 @@ def test_two_rank_sharded_signature_equals_single_engine(tmp_path, world, total_
     shards = [np.load(os.path.join(str(tmp_path), "rank%d.npz" % r)) for r in range(world)]
     assert sum(int(s["lanes"]) for s in shards) == total_lanes
     assert [int(s["off"]) for s in shards] == [0, int(shards[0]["lanes"]) // 64]
+    seq = circuits.lfsr_pipeline(n_lfsr=4, lfsr_bits=8, stages=24, taps=(7, 5, 1, 0))
+    ser = B200Engine(seq, 1, True, lanes=total_lanes, runtime=CpuRuntime(), keep="ports", mode="serial")
+    ser.randomize_inputs(["/l%d_q%d/out" % (n, b) for n in range(4) for b in (0, 3)])
+    ser.run(21)
+    spc, scs = ser.signature()
+    assert spc.sum() > 0
     for s in shards:                       # every rank holds the reduced (global) vectors
         assert np.array_equal(s["pc"], pc) and np.array_equal(s["cs"], cs)
         assert int(s["tg"][0]) == 6 * total_lanes
+        assert str(s["smode"]) == "serial" and np.array_equal(s["spc"], spc) and np.array_equal(s["scs"], scs)
 
 
 def test_shard_lanes_geometry():
