@@ -1291,10 +1291,28 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
                     for (int u = 0; u < n; ++u) {
                         const uint4 r = recs[f + u];
                         const uint32_t flags = r.x >> 24;
-                        const W a = stream_operand_bf<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
-                        const W bb = stream_operand_bf<W, UNIFIED>((r.y >> 27) & 7u, r.y & STR_M24, rows, stash, cols, acc, greg, active);
-                        const W c = stream_operand_bf<W, UNIFIED>((r.z >> 24) & 7u, r.z & STR_M24, rows, stash, cols, acc, greg, active);
-                        const W res = apply_op_w<W>((flags & 15u) | ((flags & 16u) << 3), a, bb, c);
+                        // one dispatch per record (on the opcode); only the operands the opcode has are fetched
+#define MCB_FA stream_operand_bf<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active)
+#define MCB_FB stream_operand_bf<W, UNIFIED>((r.y >> 27) & 7u, r.y & STR_M24, rows, stash, cols, acc, greg, active)
+#define MCB_FC stream_operand_bf<W, UNIFIED>((r.z >> 24) & 7u, r.z & STR_M24, rows, stash, cols, acc, greg, active)
+                        W res;
+                        switch (flags & 15u) {
+                            case MCB_OP_BUF:  res = MCB_FA; break;
+                            case MCB_OP_AND:  { const W a = MCB_FA, b = MCB_FB; res = a & b; } break;
+                            case MCB_OP_OR:   { const W a = MCB_FA, b = MCB_FB; res = a | b; } break;
+                            case MCB_OP_XOR:  { const W a = MCB_FA, b = MCB_FB; res = a ^ b; } break;
+                            case MCB_OP_ANDN: { const W a = MCB_FA, b = MCB_FB; res = a & (W)~b; } break;
+                            case MCB_OP_MUX:  { const W a = MCB_FA, b = MCB_FB, c = MCB_FC; res = (a & b) | ((W)~a & c); } break;
+                            case MCB_OP_AND3: { const W a = MCB_FA, b = MCB_FB, c = MCB_FC; res = a & b & c; } break;
+                            case MCB_OP_OR3:  { const W a = MCB_FA, b = MCB_FB, c = MCB_FC; res = a | b | c; } break;
+                            case MCB_OP_XOR3: { const W a = MCB_FA, b = MCB_FB, c = MCB_FC; res = a ^ b ^ c; } break;
+                            case MCB_OP_MAJ:  { const W a = MCB_FA, b = MCB_FB, c = MCB_FC; res = (a & b) | (a & c) | (b & c); } break;
+                            default:          res = 0; break;
+                        }
+#undef MCB_FA
+#undef MCB_FB
+#undef MCB_FC
+                        if (flags & 16u) res = (W)~res;
                         if ((flags & 32u) && active) cols.st(r.w & STR_M24, res);
                         const uint32_t so = r.w >> 24;
                         if (so) stash_w[(so - 1) * STR_NT] = res;

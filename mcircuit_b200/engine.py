@@ -116,10 +116,9 @@ class B200Engine(Executor):
                         info = stream.serial_info
                         n_rec = max(1, info["records"])
                         registers = info["mux_chain_units"] + 2 * info["xor_mux_units"] >= 0.5 * n_rec
-                        # ... or, at large lane counts (where the resident kernel's time grows with the lanes and the
-                        # stream's does not), a stream whose operands are mostly forwarded through registers / stash
-                        forwarded = (self.words >= 4096 and info["tma_boxes"] <= 0.25 * n_rec and
-                                     info["late_operands"] <= 0.05 * n_rec)
+                        # ... or a stream whose operands are mostly forwarded through registers / stash (gate-level
+                        # flip-flops, ripple carries): few TMA boxes, hardly any late load
+                        forwarded = info["tma_boxes"] <= 0.25 * n_rec and info["late_operands"] <= 0.05 * n_rec
                         if registers or forwarded:
                             program = stream
                     except compiler.CircuitError:

@@ -231,7 +231,8 @@ def test_auto_mode_policy():
     def mode_of(root, lanes):
         return B200Engine(root, 1, True, lanes=lanes, runtime=CpuRuntime(), keep="ports").mode
     assert mode_of(circuits.lfsr_pipeline(MD, 8, 16, 60, taps=(15, 13, 12, 10)), 64 * 16) == "serial"
+    assert mode_of(circuits.gate_level_lfsr(MD, n_bits=32, taps=(31, 21, 1, 0), stages=64), 64 * 16) == "serial"   # forwarded
+    assert mode_of(circuits.gate_level_lfsr(MD), 64 * 16) == "resident"        # too short to stage its state: late loads
     assert mode_of(circuits.counter_circuit(MD), 64) == "resident"
-    assert mode_of(circuits.array_multiplier(MD, 8), 64 * 16) == "resident"
-    assert mode_of(circuits.gate_level_lfsr(MD), 64 * 16) == "resident"
+    assert mode_of(circuits.array_multiplier(MD, 16), 64 * 16) == "resident"   # scattered operands: a box per operand
     assert mode_of(circuits.random_dag(MD, n_gates=6000, depth=12, n_inputs=64, seed=5), 64 * 64) == "levels"
