@@ -99,8 +99,8 @@ int mcb_run(const uint32_t *d_records, const int32_t *h_level_off, int n_levels,
 /* K3 - streamed serial run.  Replaces `step()` / `burst()` (core/simulator.py:195-245, :293-297)
  * in the reference's own execution model: every micro-op in emit order, in place, `steps` times,
  * each consumer thread on its own (slice of a) lane column, ONE launch for any number of steps.
- * `d_stream` (16-byte aligned) holds `n_blocks` control lines of 192 words (mcircuit_b200/serial.py):
- * 4 meta words, 12 segment words, 16 TMA runs, 32 row slots, 32 records of four
+ * `d_stream` (16-byte aligned) holds `n_blocks` control lines of 204 words (mcircuit_b200/serial.py):
+ * 4 meta words, 16 TMA runs, 24 segment words, 32 row slots, 32 records of four
  * `field(24) | meta(8) << 24` words.  A producer warp per CTA stages each block's control line
  * (cp.async.bulk) and its state rows (one cp.async.bulk.tensor.2d per run of 2^k consecutive slots;
  * the tensor maps of the state planes are encoded and cached inside the library) into a

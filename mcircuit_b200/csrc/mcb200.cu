@@ -1021,7 +1021,7 @@ static int launch_resident(const uint4 *recs, int n_recs, const View &v, long lo
 // the rules that decide which rows may be staged ahead of time.
 //
 // CTA = 4 consumer warps (128 columns) + 1 producer warp.  The producer walks the stream ahead of
-// the consumers: per block (up to 32 records) it stages the block's 768-byte control line
+// the consumers: per block (up to 32 records) it stages the block's 816-byte control line
 // (cp.async.bulk) and every state row the block reads - one cp.async.bulk.tensor.2d per run of
 // 2^k consecutive slots, a [2^k rows x 128 columns] box of the state plane described by a tensor
 // map - into one of `n_groups` shared-memory ring groups, completion on the group's `full`
@@ -1041,15 +1041,15 @@ static int launch_resident(const uint4 *recs, int n_recs, const View &v, long lo
 // ------------------------------------------------------------------------------------------
 #define STR_BLOCK 32
 #define STR_RING_ROWS 32
-#define STR_MAX_SEG 12
+#define STR_MAX_SEG 24
 #define STR_MAX_RUNS 16
-#define STR_W_SEG 4
-#define STR_W_RUN 16
-#define STR_W_SLOT 32
-#define STR_W_REC 64
-#define STR_WORDS 192                       // uint32 per control line
-#define STR_CTRL_BYTES 768
-#define STR_CTRL_PITCH 768
+#define STR_W_RUN 4                         // meta and runs first: one word per producer lane
+#define STR_W_SEG 20
+#define STR_W_SLOT 44
+#define STR_W_REC 76
+#define STR_WORDS 204                       // uint32 per control line
+#define STR_CTRL_BYTES 816
+#define STR_CTRL_PITCH 896                  // ring rows start 128-byte aligned
 #define STR_STASH 32
 #define STR_CONSUMER_WARPS 4
 #define STR_NT (32 * STR_CONSUMER_WARPS)    // columns per CTA
@@ -1180,7 +1180,7 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
         int b = 0, pb = 0;                       // block being issued / next block to prefetch
         long long step = 0, pstep = 0;
         bool refill = true;
-        const bool my_word = lane < STR_W_SLOT;
+        const bool my_word = lane < STR_W_SEG;          // meta + runs
         while (step < steps) {
             if (refill) {
                 pb = b;
@@ -1274,6 +1274,19 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
 #undef MCB_MUX_STEP
                     acc = d;
                     if (so) stash_w[(so - 1) * STR_NT] = acc;      // a pattern segment ends where a value goes to the stash
+                } else if (kind == SEG_XM && (sw & (1u << 25))) {
+                    // stages whose q does not come through the ring: fetched per stage as its XOR record says
+                    W d = acc;
+                    const W *ow = rows + r0 * STR_NT;
+                    const uint32_t *sl = ctl + STR_W_SLOT + r0;
+                    for (int u = 0; u < n; ++u) {
+                        const uint4 x = recs[f + 2 * u];
+                        const W q = stream_operand_bf<W, UNIFIED>((x.y >> 27) & 7u, x.y & STR_M24, rows, stash, cols, acc, greg, active);
+                        d = (greg & (d ^ q)) | ((W)~greg & ow[u * STR_NT]);
+                        if (active) cols.st(sl[u], d);
+                    }
+                    acc = d;
+                    if (so) stash_w[(so - 1) * STR_NT] = acc;
                 } else if (kind == SEG_XM) {
                     const W *qw = rows + r0 * STR_NT, *ow = qw + n * STR_NT;
                     const uint32_t *sl = ctl + STR_W_SLOT + r0 + n;

@@ -40,12 +40,13 @@ visible to TMA reads only after a ``fence.proxy.async`` - executed at the start 
 ``STASH``, ``ACC`` or ``LATE`` (an ordinary load at the point of use, always correct for a thread's
 own column).
 
-Stream: one 768-byte control line per block = 192 words:
+Stream: one 816-byte control line per block = 204 words (what the producer needs comes first):
   m0 = ring rows | flags << 8 (1 = ends in a GUARD segment, 2 = FENCE first) | segments << 16 | runs << 24
   m1 = blocks to jump when the guard's enable is zero everywhere;  m2 = records;  m3 = 0
-  seg[12] = kind(2) | count << 2 | first record << 8 | first ring row << 13 | (stash entry + 1) << 18 | head is ACC << 24
-            (count: units of a pattern; a pattern segment ends at a unit whose result also goes to the stash)
   run[16] = first slot | (first ring row | log2(rows) << 5) << 24     (2^k consecutive slots = one TMA box)
+  seg[24] = kind(2) | count << 2 | first record << 8 | first ring row << 13 | (stash entry + 1) << 18 | head is ACC << 24
+            | q by record << 25
+            (count: units of a pattern; a pattern segment ends at a unit whose result also goes to the stash)
   slot[32] = slot of ring row j
   32 records of four words:
     w0 = a field | op(4) << 24 | neg << 28 | store << 29
@@ -54,7 +55,9 @@ Stream: one 768-byte control line per block = 192 words:
     w3 = out slot | (stash entry + 1) << 24
   field = ring row (RING), slot (LATE), stash entry (STASH).
 Pattern segments use canonical rows: MUX unit u reads ring row ``first + u`` and stores to that row's slot;
-XM stage u of n reads rows ``first + u`` (q) and ``first + n + u`` (old value, and the slot it stores to).
+XM stage u of n reads rows ``first + u`` (q) and ``first + n + u`` (old value, and the slot it stores to); an XM
+segment flagged "q by record" takes each stage's q from wherever its XOR record says (stash, late load) and has
+only the n old-value rows, ``first + u``.
 """
 from __future__ import annotations
 
@@ -72,9 +75,9 @@ K_NONE, K_RING, K_LATE, K_ACC, K_GREG, K_STASH = 0, 1, 2, 3, 4, 5
 SEG_GENERIC, SEG_MUX, SEG_XM, SEG_GUARD = 0, 1, 2, 3
 BLOCK = 32                 # records per block
 RING_ROWS = 32             # rows one block can stage
-MAX_SEG = 12
+MAX_SEG = 24
 MAX_RUNS = 16
-W_SEG, W_RUN, W_SLOT, W_REC = 4, 4 + MAX_SEG, 4 + MAX_SEG + MAX_RUNS, 4 + MAX_SEG + MAX_RUNS + RING_ROWS
+W_RUN, W_SEG, W_SLOT, W_REC = 4, 4 + MAX_RUNS, 4 + MAX_RUNS + MAX_SEG, 4 + MAX_RUNS + MAX_SEG + RING_ROWS
 BLOCK_WORDS = W_REC + 4 * BLOCK
 GB_MAX = 8                 # ring groups (blocks in flight) the kernel uses at most
 FENCE_PERIOD = 4           # every block b with b % FENCE_PERIOD == 0 starts with fence.proxy.async
@@ -94,7 +97,7 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
                    adder_prefix: bool = False) -> Program:
     """Lower ``design`` to a serial program.  ``keep`` / ``observe`` as in
     ``compiler.compile_design``; the result is a ``Program`` with ``serial=True`` whose
-    ``records`` are the control lines described in the module docstring (``uint32[n_blocks, 192]``).
+    ``records`` are the control lines described in the module docstring (``uint32[n_blocks, 204]``).
     ``guard`` / ``patterns`` / ``stash`` / ``ring`` switch the optimisations off one by one (tests, sweeps);
     the results are the same."""
     if keep not in ("all", "ports"):
@@ -352,9 +355,8 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
             if (code[i] == OP_XOR and cls[i + 1] == "M" and region_of[i + 1] == region_of[i] and elide[i]
                     and i not in stash_of and served[i + 1][1] == K_ACC and n_reads[OUT[i]] == 1):
                 sa, sb = served[i][0], served[i][1]
-                mem = B[i] if (sa == K_ACC and sb is None) else (A[i] if (sb == K_ACC and sa is None) else -1)
-                if mem >= 0 and ring_ok(int(sig_slot[mem]), i):
-                    cls[i] = "X"
+                if (sa == K_ACC) != (sb == K_ACC) and K_GREG not in (sa, sb):
+                    cls[i] = "X"                     # the other operand: a ring row, a stash word or a late load
                     cls[i + 1] = "m"
 
     # ---- blocks: segments of records, ring rows, TMA runs ------------------------------------------------------
@@ -512,7 +514,7 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
                 n_late += 1
             else:
                 n_stash += 1
-            cur.segs.append([SEG_GUARD, 1, len(cur.recs), 0, 0])
+            cur.segs.append([SEG_GUARD, 1, len(cur.recs), 0, 0, False])
             cur.recs.append([f | (OP_GUARD << 24), kind << 24, 0, 0])
             cur.guard = k
             n_seg_kind[SEG_GUARD] += 1
@@ -539,7 +541,7 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
                 for f in head_rows:                          # the head's own data row goes in front of the segment
                     cur.row_of[f] = len(cur.rows)
                     cur.rows.append(f)
-                cur.segs.append([SEG_MUX, 0, len(cur.recs), len(cur.rows), 0])
+                cur.segs.append([SEG_MUX, 0, len(cur.recs), len(cur.rows), 0, False])
                 cur.sealed = False
                 n_seg_kind[SEG_MUX] += 1
             seg = cur.segs[-1]
@@ -558,38 +560,53 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
             continue
         if c == "X":
             for attempt in (0, 1):
-                px, pm = operand_plan(i), operand_plan(i + 1)
+                px = operand_plan(i)
                 last_seg = cur.segs[-1] if cur.segs else None
-                extend = (last_seg is not None and last_seg[0] == SEG_XM and not cur.sealed and
-                          last_seg[2] + 2 * last_seg[1] == len(cur.recs) and last_seg[3] + 2 * last_seg[1] == len(cur.rows))
                 q_idx = 1 if px[0][0] == K_ACC else 0
-                q_slot, old_slot = px[q_idx][1], int(sig_slot[OUT[i + 1]])
-                ok_kinds = px[q_idx][0] == K_RING and px[1 - q_idx][0] == K_ACC
+                q_kind, q_field = px[q_idx]
+                old_slot = int(sig_slot[OUT[i + 1]])
+                ok_kinds = px[1 - q_idx][0] == K_ACC and q_kind in (K_RING, K_STASH, K_LATE) and old_slot not in cur.stored
                 if not ok_kinds:
                     break
-                # canonical rows of a stage segment: all q rows, then all old rows (the olds are consecutive slots)
-                if extend:
-                    at = last_seg[3] + last_seg[1]
-                    tentative = cur.rows[:at] + [q_slot] + cur.rows[at:] + [old_slot]
+                by_record = q_kind != K_RING               # the stage's q does not come through the ring
+                if by_record:
+                    extend = (last_seg is not None and last_seg[0] == SEG_XM and last_seg[5] and not cur.sealed and
+                              last_seg[2] + 2 * last_seg[1] == len(cur.recs) and last_seg[3] + last_seg[1] == len(cur.rows))
+                    tentative = cur.rows + [old_slot]
                 else:
-                    tentative = cur.rows + [q_slot, old_slot]
+                    extend = (last_seg is not None and last_seg[0] == SEG_XM and not last_seg[5] and not cur.sealed and
+                              last_seg[2] + 2 * last_seg[1] == len(cur.recs) and last_seg[3] + 2 * last_seg[1] == len(cur.rows))
+                    # canonical rows of a stage segment: all q rows, then all old rows (the olds are consecutive slots)
+                    if extend:
+                        at = last_seg[3] + last_seg[1]
+                        tentative = cur.rows[:at] + [q_field] + cur.rows[at:] + [old_slot]
+                    else:
+                        tentative = cur.rows + [q_field, old_slot]
                 if cur.fits_rows(2, tentative, not extend):
                     break
                 close()
             if ok_kinds:
                 if not extend:
-                    cur.segs.append([SEG_XM, 0, len(cur.recs), len(cur.rows), 0])
+                    cur.segs.append([SEG_XM, 0, len(cur.recs), len(cur.rows), 0, by_record])
                     cur.sealed = False
                     n_seg_kind[SEG_XM] += 1
                 seg = cur.segs[-1]
-                cur.rows.insert(seg[3] + seg[1], q_slot)
-                cur.rows.append(old_slot)
+                if by_record:
+                    cur.rows.append(old_slot)
+                    n_ring += 1
+                    n_stash += q_kind == K_STASH
+                    n_late += q_kind == K_LATE
+                else:
+                    cur.rows.insert(seg[3] + seg[1], q_field)
+                    cur.rows.append(old_slot)
+                    n_ring += 2
+                    q_field = 0
                 pattern_row = {}
-                # records: XOR(acc, q); MUX(G, acc, old) -> out; their rows are the segment's by convention
+                # records: XOR(acc, q); MUX(G, acc, old) -> out; ring rows are the segment's by convention
                 block_of_op[i] = block_of_op[i + 1] = len(blocks)
                 if cur.first_op < 0:
                     cur.first_op = i
-                cur.recs.append([0 | (OP_XOR << 24), 0 | ((K_ACC | (K_RING << 3)) << 24), 0, 0])
+                cur.recs.append([0 | (OP_XOR << 24), q_field | ((K_ACC | (q_kind << 3)) << 24), 0, 0])
                 out_slot = old_slot
                 stash_out = stash_of[i + 1] + 1 if (i + 1) in stash_of else 0
                 cur.recs.append([0 | ((OP_MUX | F_STORE) << 24), 0 | ((K_GREG | (K_ACC << 3)) << 24),
@@ -597,7 +614,6 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
                 cur.stored.add(out_slot)
                 n_acc += 2
                 n_greg += 1
-                n_ring += 2
                 n_elided += 1
                 seg[1] += 1
                 if (i + 1) in stash_of:
@@ -618,7 +634,7 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
                 break
             close()
         if not extend:
-            cur.segs.append([SEG_GENERIC, 0, len(cur.recs), 0, 0])
+            cur.segs.append([SEG_GENERIC, 0, len(cur.recs), 0, 0, False])
             n_seg_kind[SEG_GENERIC] += 1
         pattern_row = {}
         add_record(i, plan, SEG_GENERIC, False)
@@ -641,10 +657,10 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
             stream[b, 1] = last_block - b                    # blocks b+1 .. last_block are the region
         stream[b, 0] = len(blk.rows) | flags | (len(blk.segs) << 16) | (len(runs) << 24)
         stream[b, 2] = len(blk.recs)
-        for k, (kind, count, first_rec, first_row, stash_out) in enumerate(blk.segs):
+        for k, (kind, count, first_rec, first_row, stash_out, by_record) in enumerate(blk.segs):
             head_acc = kind == SEG_MUX and ((blk.recs[first_rec][1] >> 27) & 7) == K_ACC
             stream[b, W_SEG + k] = (kind | (count << 2) | (first_rec << 8) | (first_row << 13) | (stash_out << 18) |
-                                    (int(head_acc) << 24))
+                                    (int(head_acc) << 24) | (int(bool(by_record)) << 25))
         for k, (first_row, lg) in enumerate(runs):
             stream[b, W_RUN + k] = blk.rows[first_row] | ((first_row | (lg << 5)) << 24)
         stream[b, W_SLOT:W_SLOT + len(blk.rows)] = blk.rows
@@ -706,7 +722,7 @@ def decode_block(line):
                      "fields": (w0 & 0xFFFFFF, w1 & 0xFFFFFF, w2 & 0xFFFFFF), "out": w3 & 0xFFFFFF,
                      "stash_out": (w3 >> 24) - 1, "kinds": ((w1 >> 24) & 7, (w1 >> 27) & 7, (w2 >> 24) & 7)})
     segs = [{"kind": x & 3, "count": (x >> 2) & 63, "first_rec": (x >> 8) & 31, "first_row": (x >> 13) & 31,
-             "stash_out": ((x >> 18) & 63) - 1} for x in w[W_SEG:W_SEG + n_seg]]
+             "stash_out": ((x >> 18) & 63) - 1, "q_by_record": bool((x >> 25) & 1)} for x in w[W_SEG:W_SEG + n_seg]]
     runs = [{"slot": x & 0xFFFFFF, "first_row": (x >> 24) & 31, "rows": 1 << (x >> 29)} for x in w[W_RUN:W_RUN + n_runs]]
     return {"n_rows": n_rows, "guard": bool(w[0] & M_GUARD), "fence": bool(w[0] & M_FENCE), "span": w[1],
             "rows": w[W_SLOT:W_SLOT + n_rows], "segments": segs, "runs": runs, "records": recs}

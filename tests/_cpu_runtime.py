@@ -252,6 +252,14 @@ class CpuRuntime:
                             acc = d
                             if seg["stash_out"] >= 0:         # only the segment's last value can go to the stash
                                 stash[seg["stash_out"]] = acc
+                        elif seg["kind"] == S.SEG_XM and seg["q_by_record"]:
+                            for u in range(n):                # q from wherever the stage's XOR record says, old = row r0 + u
+                                x = recs[f + 2 * u]
+                                q = operand(x["kinds"][1], x["fields"][1])
+                                acc = (greg & (acc ^ q)) | (~greg & ring[r0 + u])
+                                store(blk["rows"][r0 + u], acc)
+                            if seg["stash_out"] >= 0:
+                                stash[seg["stash_out"]] = acc
                         elif seg["kind"] == S.SEG_XM:
                             for u in range(n):
                                 acc = (greg & (acc ^ ring[r0 + u])) | (~greg & ring[r0 + n + u])

@@ -177,7 +177,7 @@ def check_stream_invariants(prog):
             if seg["kind"] == serial.SEG_MUX:
                 st.update(blk["rows"][r0:r0 + n])
             elif seg["kind"] == serial.SEG_XM:
-                st.update(blk["rows"][r0 + n:r0 + 2 * n])
+                st.update(blk["rows"][r0:r0 + n] if seg["q_by_record"] else blk["rows"][r0 + n:r0 + 2 * n])
             elif seg["kind"] == serial.SEG_GENERIC:
                 st.update(r["out"] for r in blk["records"][f:f + n] if r["store"])
         stores.append(st)
@@ -214,10 +214,16 @@ def check_stream_invariants(prog):
                 seen_recs += n
             elif seg["kind"] == serial.SEG_XM:
                 for u in range(n):
-                    assert blk["rows"][r0 + u] not in stored and blk["rows"][r0 + n + u] not in stored
-                    assert blk["records"][f + 2 * u + 1]["out"] == blk["rows"][r0 + n + u]
+                    old_row = r0 + u if seg["q_by_record"] else r0 + n + u
+                    x = blk["records"][f + 2 * u]
+                    if seg["q_by_record"]:
+                        assert x["kinds"][1] in (serial.K_STASH, serial.K_LATE) and x["kinds"][0] == serial.K_ACC
+                    else:
+                        assert blk["rows"][r0 + u] not in stored
+                    assert blk["rows"][old_row] not in stored
+                    assert blk["records"][f + 2 * u + 1]["out"] == blk["rows"][old_row]
                     assert blk["records"][f + 2 * u + 1]["stash_out"] == (seg["stash_out"] if u == n - 1 else -1)
-                    stored.add(blk["rows"][r0 + n + u])
+                    stored.add(blk["rows"][old_row])
                 seen_recs += 2 * n
             else:
                 for rec in blk["records"][f:f + n]:
