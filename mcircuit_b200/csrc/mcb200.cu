@@ -1050,10 +1050,10 @@ static int launch_resident(const uint4 *recs, int n_recs, const View &v, long lo
 #define STR_WORDS 204                       // uint32 per control line
 #define STR_CTRL_BYTES 816
 #define STR_CTRL_PITCH 896                  // ring rows start 128-byte aligned
-#define STR_STASH 32
+#define STR_STASH 48
 #define STR_CONSUMER_WARPS 4
 #define STR_NT (32 * STR_CONSUMER_WARPS)    // columns per CTA
-#define STR_GB_MAX 8
+#define STR_GB_MAX 6
 #define STR_PD 4                            // control lines the producer keeps in registers ahead of its issue point
 #define STR_HEAD_BYTES 1024                 // barriers and votes
 #define STR_M24 0x00ffffffu

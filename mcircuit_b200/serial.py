@@ -79,11 +79,11 @@ MAX_SEG = 24
 MAX_RUNS = 16
 W_RUN, W_SEG, W_SLOT, W_REC = 4, 4 + MAX_RUNS, 4 + MAX_RUNS + MAX_SEG, 4 + MAX_RUNS + MAX_SEG + RING_ROWS
 BLOCK_WORDS = W_REC + 4 * BLOCK
-GB_MAX = 8                 # ring groups (blocks in flight) the kernel uses at most
-FENCE_PERIOD = 4           # every block b with b % FENCE_PERIOD == 0 starts with fence.proxy.async
+GB_MAX = 6                 # ring groups (blocks in flight) the kernel uses at most
+FENCE_PERIOD = 2           # every block b with b % FENCE_PERIOD == 0 starts with fence.proxy.async
 RING_DISTANCE = BLOCK * (GB_MAX + FENCE_PERIOD + 1)
-STASH_N = 32               # per-thread shared-memory forwarding words
-STASH_WINDOW = 512         # micro-ops between a stashed result and its last reader, at most
+STASH_N = 48               # per-thread shared-memory forwarding words
+STASH_WINDOW = RING_DISTANCE   # micro-ops between a stashed result and its last reader, at most: beyond it the ring can stage the row
 SLOT_LIMIT = 1 << 24
 F_NEG, F_STORE = 1 << 4, 1 << 5
 M_GUARD, M_FENCE = 1 << 8, 1 << 9
