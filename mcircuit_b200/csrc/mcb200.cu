@@ -756,6 +756,12 @@ struct GlobalCols {
         // (5-7 instructions per row address instead of one IMAD.WIDE on a base register)
         asm volatile("" : "+l"(base_p), "+l"(base_s), "+r"(stride_p), "+r"(stride_s));
     }
+    // every row of this thread becomes one private dummy word (threads beyond the last lane column: their loads and
+    // stores then need no predicate at all)
+    __device__ __forceinline__ void park(void *dummy) {
+        base_p = base_s = reinterpret_cast<char *>(dummy);
+        stride_p = stride_s = 0;
+    }
     __device__ __forceinline__ W *at(uint32_t slot) const {
         if (UNIFIED) return reinterpret_cast<W *>(base_p + (unsigned long long)slot * stride_p);
         return reinterpret_cast<W *>(slot < n_persist ? base_p + (unsigned long long)slot * stride_p
@@ -1149,7 +1155,7 @@ template <typename W, bool UNIFIED>
 __global__ void __launch_bounds__(32 * (STR_CONSUMER_WARPS + 1), 1)
 k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long long steps, long long n_cols,
              const unsigned char *__restrict__ tmaps, unsigned long long *__restrict__ skipped, int n_groups,
-             int ring_rows) {
+             int ring_rows, unsigned char *__restrict__ parking) {
     extern __shared__ __align__(128) unsigned char smem[];
     StreamSmem *sh = reinterpret_cast<StreamSmem *>(smem);
     W *stash_base = reinterpret_cast<W *>(smem + STR_HEAD_BYTES);
@@ -1238,8 +1244,10 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
 
     // ---------------- consumers ----------------
     const long long col = c0 + tid;
-    const bool active = col < n_cols;
-    const GlobalCols<W, UNIFIED> cols(v, col);
+    const bool in_range = col < n_cols;
+    GlobalCols<W, UNIFIED> cols(v, col);
+    if (!in_range) cols.park(parking + tid * 8);     // only in the last CTA: garbage in, garbage out, into a private word
+    constexpr bool active = true;                    // ... so no load or store below is predicated
     const W *stash = stash_base + tid;
     W *stash_w = stash_base + tid;
     W acc = 0, greg = 0;
@@ -1338,7 +1346,7 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
                 const uint4 r = recs[guard_rec];
                 greg = stream_operand<W, UNIFIED>((r.y >> 24) & 7u, r.x & STR_M24, rows, stash, cols, acc, greg, active);
                 fence_async_global();                    // everything stored so far becomes visible to later TMA reads
-                const uint32_t any = __any_sync(0xffffffffu, active && greg != 0);
+                const uint32_t any = __any_sync(0xffffffffu, in_range && greg != 0);
                 __syncwarp();
                 if (lane == 0) {
                     sh->votes[gidx][warp] = any;
@@ -1500,6 +1508,17 @@ static int launch_stream_w(const uint32_t *stream, int n_blocks, int ring_rows, 
     if (g_tune.stream_groups > 0 && groups > g_tune.stream_groups) groups = g_tune.stream_groups;
     if (groups < 2) return fail(MCB_ERR_ARG, "shared memory too small for the stream ring");
     const size_t smem = fixed + (size_t)groups * group_bytes;
+    static std::atomic<unsigned char *> parking[64];          // per device: 8 bytes per consumer thread
+    unsigned char *park = parking[dev & 63].load(std::memory_order_acquire);
+    if (!park) {
+        CUDA_TRY(cudaMalloc(&park, 4096));
+        CUDA_TRY(cudaMemset(park, 0, 4096));
+        unsigned char *expected = nullptr;
+        if (!parking[dev & 63].compare_exchange_strong(expected, park)) {
+            cudaFree(park);
+            park = expected;
+        }
+    }
     auto kern = unified ? k_run_stream<W, true> : k_run_stream<W, false>;
     // the attribute is per device and per instantiation (W is a template parameter of this function)
     static std::atomic<size_t> smem_set[2][64];
@@ -1509,7 +1528,7 @@ static int launch_stream_w(const uint32_t *stream, int n_blocks, int ring_rows, 
         done.store(smem, std::memory_order_release);
     }
     kern<<<(unsigned)grid, 32 * (STR_CONSUMER_WARPS + 1), smem, s>>>(stream, n_blocks, v, steps, cols, d_maps, d_skipped,
-                                                                     groups, ring_rows);
+                                                                     groups, ring_rows, park);
     LAUNCH_CHECK("k_run_stream");
     return 0;
 }
