@@ -1265,8 +1265,11 @@ k_run_stream(const uint32_t *__restrict__ stream, int n_blocks, View v, long lon
             if (m.x & 0x200u) fence_async_global();
             const uint32_t n_seg = (m.x >> 16) & 0xffu;
             uint32_t guard_rec = 0;
+            uint32_t sw_next = ctl[STR_W_SEG];
             for (uint32_t k = 0; k < n_seg; ++k) {
-                const uint32_t sw = ctl[STR_W_SEG + k];
+                const uint32_t sw = sw_next;
+                sw_next = ctl[STR_W_SEG + k + 1];        // the next segment's word, off this segment's critical path
+                                                         // (one word past the table is the first row slot: harmless)
                 const uint32_t kind = sw & 3u, f = (sw >> 8) & 31u, r0 = (sw >> 13) & 31u, so = (sw >> 18) & 63u;
                 int n = (int)((sw >> 2) & 63u);
                 if (kind == SEG_MUX) {
