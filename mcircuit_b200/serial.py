@@ -62,13 +62,12 @@ only the n old-value rows, ``first + u``.
 from __future__ import annotations
 
 from bisect import bisect_left, bisect_right
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, List, Sequence
 
 import numpy as np
 
 from . import compiler
-from .compiler import (OP_ARITY, OP_BUF, OP_MUX, OP_NEG, OP_NOP, OP_XOR, CircuitError, Program,
-                       _Instance, _type_name)
+from .compiler import OP_ARITY, OP_MUX, OP_NEG, OP_XOR, CircuitError, Program, _Instance, _type_name
 
 OP_GUARD = 11
 K_NONE, K_RING, K_LATE, K_ACC, K_GREG, K_STASH = 0, 1, 2, 3, 4, 5
@@ -117,7 +116,6 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
     written = bytearray(n_sig)
     last_read = [-1] * n_sig
     n_reads = [0] * n_sig
-    first_read = [n_ops] * n_sig
     first_write = [n_ops] * n_sig
     last_write = [-1] * n_sig
     for i in range(n_ops):
@@ -129,8 +127,6 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
                 state_read[s] = 1
             last_read[s] = i
             n_reads[s] += 1
-            if first_read[s] == n_ops:
-                first_read[s] = i
         o = OUT[i]
         written[o] = 1
         if first_write[o] == n_ops:
@@ -157,15 +153,6 @@ def compile_serial(design, keep="all", observe: Sequence[str] = (), share_edge_d
             for s in range(base, base + design.pin_width[pin]):
                 persistent[s] = 1
                 kept[s] = True
-
-    # ---- store elision: a transient result whose only readers are the very next record ------------
-    def next_only(i):
-        o = OUT[i]
-        if persistent[o] or n_writers[o] != 1:
-            return False
-        if n_reads[o] == 0:
-            return True                                    # dead value: computed, never stored
-        return first_read[o] == i + 1 and last_read[o] == i + 1
 
     # ---- guarded regions ---------------------------------------------------------------------------------
     region_of = [-1] * n_ops                 # op -> region index
