@@ -783,19 +783,18 @@ class B200Engine(Executor):
         """Rebuild this engine WITHOUT shared edge detectors, keeping all state: called when a caller pokes the
         ``prevclock`` pin of one Register / Counter of a sharing group, which the shared bit cannot represent
         (in the reference every primitive has its own ``prevclock`` global, simulator.py:100-127)."""
+        if self._toggle is not None:                             # its shadow rows are laid out for the shared program
+            raise compiler.CircuitError("toggle counting is on and one member's prevclock of a shared group is being "
+                                        "poked: build the engine with share_edge_detectors=False")
         kw = dict(self._ctor_kwargs)
         kw["share_edge_detectors"] = False
         if self.mode == "serial" or kw.get("mode") == "serial":
             kw["mode"] = "serial"
         new = B200Engine(self.root, self.burst_size, self.map_pins, runtime=self.rt, **kw)
         new.load_state_dict(self.state_dict())
-        toggle = self._toggle
         self.close()
         self.__dict__.update(new.__dict__)
         new._d_records = None                                    # its graphs and buffers are ours now
-        if toggle is not None:
-            raise CircuitError("toggle counting and an individual prevclock poke in a shared group: rebuild the engine "
-                               "with share_edge_detectors=False first")
 
     def regions_skipped(self) -> int:
         """Serial mode: how many guarded regions the first warp jumped over so far (a sample of

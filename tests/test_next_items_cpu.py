@@ -236,3 +236,14 @@ def test_auto_mode_policy():
     assert mode_of(circuits.counter_circuit(MD), 64) == "resident"
     assert mode_of(circuits.array_multiplier(MD, 16), 64 * 16) == "resident"   # scattered operands: a box per operand
     assert mode_of(circuits.random_dag(MD, n_gates=6000, depth=12, n_inputs=64, seed=5), 64 * 64) == "levels"
+
+
+def test_prevclock_poke_with_toggle_counting_is_refused_cleanly():
+    root = circuits.lfsr_pipeline(MD, 3, 8, 6, taps=(7, 5, 1, 0))
+    eng = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), mode="serial")
+    eng.enable_toggle_counts(["/tap0/pin"])
+    eng.run(3)
+    with pytest.raises(compiler.CircuitError):
+        eng.set_pin_state("/l1_q4/prevclock", 1)
+    assert eng.program.shared_prev and eng.steps_done == 3          # nothing was rebuilt
+    eng.run(2)                                                       # and the engine still works
