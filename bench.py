@@ -240,7 +240,8 @@ def run_reference(a):
             best = jits[c]
             break
     if best is not None:
-        value, kind, ms = best["value"], "reference_jit", 1e3 * best["seconds"] / max(1, best["burst_calls"])
+        # "reference": the reference's own implementation (its LLVM JIT from baseline/_ref), not a port
+        value, kind, ms = best["value"], "reference", 1e3 * best["seconds"] / max(1, best["burst_calls"])
         sample = ("JIT.burst() of the C5 generator at %d gates, width=%d, %d steps in %.2f s on 1 core (the reference "
                   "cannot build 10^6 gates)" % (best["gates"], best["width"], best["steps"], best["seconds"]))
         cores = 1
@@ -257,7 +258,8 @@ def run_reference(a):
                            "build; cpu_baseline.port = the reference algorithm (sequential in-place emit-order pass, "
                            "core/simulator.py:195-223) as the oracle's plain-C port on ALL host threads on the full 1M-gate "
                            "netlist - a stronger baseline than the JIT in absolute terms"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "what": "reference_jit" if kind == "reference" else "oracle/mcref.c", "sample": sample,
                          "host_cpus": os.cpu_count(), "jit": list(jits.values()), "jit_note": jit_note(), "port": port},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
