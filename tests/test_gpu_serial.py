@@ -167,3 +167,36 @@ def test_gpu_serial_tiled_lanes():
     ora.run(41)
     for p in ["/pipe_out/pin"] + [f"/tap{n}/pin" for n in range(4)]:
         assert np.array_equal(eng.get_pin_planes(p), ora.planes(p)), p
+
+
+@pytest.mark.parametrize("mode,tune", [("serial", None), ("levels", None), ("levels", ("level_tma", 1)), ("resident", None)])
+def test_gpu_kernels_never_write_outside_their_lane_columns(mode, tune):
+    """Own bounds check (compute-sanitizer is not available on this pool): with a ragged lane count the rows carry
+    padding columns up to the 128-byte stride, and the plane ends in a pad; whatever the kernels do with threads
+    beyond the last lane column (K3 parks them on a private dummy word), those words must still be zero after a
+    run - and the results must still match the oracle."""
+    root = circuits.lfsr_pipeline(MD, 6, 16, 48, taps=(15, 13, 12, 10))
+    lanes = 64 * 150                                     # 150 lane words in rows of 160
+    eng = B200Engine(root, 1, True, lanes=lanes, mode=mode, keep="ports")
+    if tune:
+        old = eng.rt.set_tuning(*tune)
+    try:
+        assert eng.stride == 160 and eng.n_tiles == 1
+        ora = cref.CRef(root, 1, True, lanes=lanes)
+        rng = np.random.default_rng(2)
+        for n in range(6):
+            v = rng.integers(0, 2, size=lanes, dtype=U64)
+            eng.set_pin_state(f"/l{n}_q0/out", v)
+            ora.set_pin_state(f"/l{n}_q0/out", v)
+        eng.run(33)
+        ora.run(33)
+        for p in eng.output_pins():
+            assert np.array_equal(eng.get_pin_planes(p), ora.planes(p)), p
+        n_rows = eng.program.n_persist + eng.program.n_scratch + 1
+        plane = eng.rt.to_host_u64(eng._plane)
+        rows = plane[:n_rows * eng.stride].reshape(n_rows, eng.stride)
+        assert not rows[:, eng.words:].any(), "a kernel wrote into the padding columns of a row"
+        assert not plane[n_rows * eng.stride:].any(), "a kernel wrote behind the last row"
+    finally:
+        if tune:
+            eng.rt.set_tuning(tune[0], old)
