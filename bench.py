@@ -365,6 +365,10 @@ def run_configs(a, dev, world, rank, jits):
             if world > 1:
                 dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            # prime the stream with ~0.1 ms of spinning so that e0, the launch(es) and e1 are all queued while the GPU is
+            # busy: the events then bracket DEVICE time, not the Python -> ctypes -> launch latency of an idle queue
+            # (which is what a 20 us single launch would otherwise measure)
+            torch.cuda._sleep(200_000)
             e0.record()
             fn()
             e1.record()
