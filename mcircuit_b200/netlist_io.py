@@ -133,8 +133,12 @@ def save_program(program, path):
         if isinstance(child, int) and type(d.leaf_desc[child]).__name__ == "ExposedPin":
             ports["in" if d.leaf_desc[child].direction == 0 else "out"].append("/%s/pin" % name)
     shadow = np.array(sorted(program.sig_shadow.items()), dtype=np.int64).reshape(-1, 2)
+    hinted = program.records_hinted if program.records_hinted is not None else np.zeros((0, 4), dtype=np.uint32)
+    info = getattr(program, "serial_info", None) or {}
     np.savez_compressed(
-        path, version=FORMAT_VERSION, records=program.records, records_hinted=program.records_hinted,
+        path, version=FORMAT_VERSION, records=program.records, records_hinted=hinted,
+        serial=bool(getattr(program, "serial", False)), n_ops=int(program.n_ops),
+        max_ring_rows=int(info.get("max_ring_rows", 0)),
         level_off=program.level_off, n_persist=program.n_persist, n_scratch=program.n_scratch,
         sig_slot=program.sig_slot[:len(program.sig_kept)], sig_kept=program.sig_kept,
         n_gates=program.n_gates, gate_words_bytes=program.gate_words_bytes, has_latch=program.has_latch,
@@ -151,14 +155,18 @@ class CachedProgram:
         from .compiler import PinNotObservable
         self._unobservable = PinNotObservable
         self.records = z["records"]
-        self.records_hinted = z["records_hinted"]
+        self.records_hinted = z["records_hinted"] if len(z["records_hinted"]) else None
+        # a stream program (mode='serial') must never be fed to the level kernels: the flag travels with the cache
+        self.serial = bool(z["serial"]) if "serial" in z.files else False
+        self.serial_info = {"max_ring_rows": int(z["max_ring_rows"])} if self.serial else None
+        self.shared_prev = None
         self.level_off = z["level_off"]
         self.n_levels = len(self.level_off) - 1
         self.n_persist, self.n_scratch = int(z["n_persist"]), int(z["n_scratch"])
         self.sig_slot, self.sig_kept = z["sig_slot"], z["sig_kept"]
         self.n_gates, self.gate_words_bytes = int(z["n_gates"]), int(z["gate_words_bytes"])
         self.has_latch = bool(z["has_latch"])
-        self.n_ops = len(self.records)
+        self.n_ops = int(z["n_ops"]) if "n_ops" in z.files else len(self.records)
         self.constants = [(int(a), int(b), int(c)) for a, b, c in z["constants"]]
         self.sig_shadow = {int(a): int(b) for a, b in z["shadow"]}
         self._pins = {str(p): (int(b), int(w)) for p, b, w in zip(z["pin_paths"], z["pin_base"], z["pin_width"])}

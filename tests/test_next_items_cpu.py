@@ -247,3 +247,25 @@ def test_prevclock_poke_with_toggle_counting_is_refused_cleanly():
         eng.set_pin_state("/l1_q4/prevclock", 1)
     assert eng.program.shared_prev and eng.steps_done == 3          # nothing was rebuilt
     eng.run(2)                                                       # and the engine still works
+
+
+def test_program_cache_of_a_stream_program(tmp_path):
+    """A cached serial (K3) program keeps its kind: it runs in mode 'serial' and gives the same results."""
+    from mcircuit_b200 import serial
+    root = circuits.lfsr_pipeline(MD, 4, 8, 20, taps=(7, 5, 1))
+    prog = serial.compile_circuit_serial(root, keep="ports", share_edge_detectors=True)
+    path = tmp_path / "stream.npz"
+    netlist_io.save_program(prog, path)
+    cached = netlist_io.load_program(path)
+    assert cached.serial and cached.records.shape == prog.records.shape
+    a = B200Engine(root, 1, True, lanes=128, runtime=CpuRuntime(), keep="ports", program=prog)
+    b = B200Engine(None, 1, True, lanes=128, runtime=CpuRuntime(), program=cached)
+    assert a.mode == b.mode == "serial"
+    with pytest.raises(ValueError):
+        B200Engine(None, 1, True, lanes=128, runtime=CpuRuntime(), program=cached, mode="levels")
+    for e in (a, b):
+        e.randomize_inputs(["/l%d_q0/out" % n for n in range(4)])
+        e.run(25)
+    for p in a.output_pins():
+        assert np.array_equal(a.get_pin_planes(p), b.get_pin_planes(p)), p
+    assert int(np.unpackbits(a.get_pin_planes("/pipe_out/pin").view(np.uint8)).sum()) > 0
