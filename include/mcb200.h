@@ -138,7 +138,9 @@ int mcb_run_pipelined(const uint32_t *d_records, const int32_t *d_level_off,
  * reference only peeks one pin at a time, core/simulator.py:285-287).  For each of `n`
  * persistent slots: d_popcount[i] = number of set lane bits, d_checksum[i] = sum over
  * columns j of word * (2 * (col_offset + j) + 1) mod 2^64.  Both are sums, so per-GPU
- * vectors combine with ncclSum.  Columns >= n_words are ignored.                         */
+ * vectors combine with ncclSum.  Columns >= n_words are ignored.  With fewer rows than the
+ * GPU needs CTAs a row is cut into column chunks whose partial sums meet by atomicAdd (the
+ * result words are zeroed on the stream first); same for the toggle counts.               */
 int mcb_signature(const int32_t *d_slots, int n, const mcb_state *st, int64_t col_offset,
                   uint64_t *d_popcount, uint64_t *d_checksum, void *stream);
 /* d_toggles[i] += popcount(word ^ shadow); shadow = word, per slot and column            */
